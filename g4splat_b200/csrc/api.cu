@@ -1,0 +1,265 @@
+// api.cu -- the C ABI declared in include/g4s_rasterizer.h.  Host orchestration only: carve the
+// caller's opaque buffers, fill argument blocks, launch on the caller's stream.
+// Replaces CR/rasterizer_impl.cu:198-448 (Rasterizer::forward / backward / markVisible) and the
+// libtorch binding RAST/rasterize_points.cu:39-254.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/g4s_rasterizer.h"
+#include "kernels.cuh"
+
+namespace g4s {
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static thread_local std::string g_error;
+
+static int fail(int code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+static int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return G4S_OK;
+    return fail(G4S_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+// debug == reference CHECK_CUDA (CR/auxiliary.h:295-302): synchronise after every stage and throw
+static int stage_check(bool debug, cudaStream_t s, const char* stage) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return check_cuda(e, stage);
+    if (debug) return check_cuda(cudaStreamSynchronize(s), stage);
+    return G4S_OK;
+}
+}  // namespace g4s
+
+using namespace g4s;
+
+extern "C" {
+
+int g4s_version(void) { return G4S_VERSION; }
+const char* g4s_last_error(void) { return g_error.c_str(); }
+int64_t g4s_launch_count(void) { return (int64_t)g_launches.load(); }
+
+size_t g4s_geom_bytes(int P) { return geom_layout(P, nullptr, nullptr); }
+size_t g4s_image_bytes(int W, int H) { return image_layout(W, H, nullptr, nullptr); }
+size_t g4s_binning_bytes(int64_t capacity) { return bin_layout(capacity, nullptr, nullptr); }
+size_t g4s_backward_scratch_bytes(int P) { return align_up((size_t)(P > 0 ? P : 1) * ACC_FLOATS * sizeof(float), 256); }
+
+int g4s_forward_plan(int P, int D, int M, int W, int H, const float* means3D, const float* shs,
+                     const float* colors_precomp, const float* opacities, const float* scales,
+                     float scale_modifier, const float* rotations, const float* transMat_precomp,
+                     const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                     float tan_fovx, float tan_fovy, int prefiltered, int* radii, void* geom_buffer,
+                     void* img_buffer, int32_t* host_counts, void* stream, int debug) {
+    (void)tan_fovx; (void)tan_fovy;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P < 0 || W <= 0 || H <= 0) return fail(G4S_EINVAL, "g4s_forward_plan: bad P/W/H");
+    if (!img_buffer || !geom_buffer) return fail(G4S_EINVAL, "g4s_forward_plan: null scratch buffer");
+    if (P > 0) {
+        if (!means3D || !opacities || !viewmatrix || !projmatrix || !radii)
+            return fail(G4S_EINVAL, "g4s_forward_plan: null required input");
+        if ((shs == nullptr) == (colors_precomp == nullptr))
+            return fail(G4S_EINVAL, "Please provide excatly one of either SHs or precomputed colors!");
+        const bool has_sr = scales != nullptr && rotations != nullptr;
+        if (has_sr == (transMat_precomp != nullptr) || ((scales != nullptr) != (rotations != nullptr)))
+            return fail(G4S_EINVAL, "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+        if (shs && !cam_pos) return fail(G4S_EINVAL, "g4s_forward_plan: campos required with SHs");
+        if (shs && (M < (D + 1) * (D + 1))) return fail(G4S_EINVAL, "g4s_forward_plan: M < (D+1)^2");
+        if (D < 0 || D > 3) return fail(G4S_EINVAL, "g4s_forward_plan: sh degree must be 0..3");
+    }
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    if (gx > 65535 || gy > 65535) return fail(G4S_EINVAL, "g4s_forward_plan: image too large");
+    GeomView geom;
+    ImageView img;
+    geom_layout(P, (char*)geom_buffer, &geom);
+    image_layout(W, H, (char*)img_buffer, &img);
+    const int T = gx * gy;
+    int rc;
+    if ((rc = check_cuda(cudaMemsetAsync(img.tile_count, 0, sizeof(uint32_t) * T, s), "memset tile_count"))) return rc;
+    if ((rc = check_cuda(cudaMemsetAsync(img.counters, 0, sizeof(int32_t) * CNT_N, s), "memset counters"))) return rc;
+
+    ProjectArgs pa;
+    pa.P = P; pa.D = D; pa.M = M; pa.W = W; pa.H = H; pa.grid_x = gx; pa.grid_y = gy; pa.prefiltered = prefiltered;
+    pa.means3D = means3D; pa.shs = shs; pa.colors_precomp = colors_precomp; pa.opacities = opacities;
+    pa.scales = scales; pa.scale_modifier = scale_modifier; pa.rotations = rotations; pa.transMat_precomp = transMat_precomp;
+    pa.view = viewmatrix; pa.proj = projmatrix; pa.campos = cam_pos;
+    pa.radii = radii; pa.geom = geom; pa.tile_count = img.tile_count; pa.counters = img.counters;
+    launch_project_fwd(pa, s);
+    if ((rc = stage_check(debug, s, "project_fwd"))) return rc;
+
+    TileScanArgs ta;
+    ta.num_tiles = T; ta.tile_count = img.tile_count; ta.tile_offset = img.tile_offset;
+    ta.tile_order = img.tile_order; ta.counters = img.counters;
+    launch_tile_scan(ta, s);
+    if ((rc = stage_check(debug, s, "tile_scan"))) return rc;
+
+    if (host_counts) {
+        if ((rc = check_cuda(cudaMemcpyAsync(host_counts, img.counters, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s),
+                             "copy counters")))
+            return rc;
+    }
+    if (debug && host_counts && prefiltered && host_counts[3] != 0)
+        return fail(G4S_ECUDA, "Point is filtered although prefiltered is set. This shouldn't happen!");
+    return G4S_OK;
+}
+
+int g4s_forward_render(int P, int W, int H, const float* background, const void* geom_buffer,
+                       void* img_buffer, void* binning_buffer, int64_t capacity, float* out_color,
+                       float* out_others, void* stream, int debug) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P < 0 || W <= 0 || H <= 0 || capacity < 0) return fail(G4S_EINVAL, "g4s_forward_render: bad sizes");
+    if (!geom_buffer || !img_buffer || !binning_buffer || !out_color || !out_others || !background)
+        return fail(G4S_EINVAL, "g4s_forward_render: null buffer");
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    GeomView geom;
+    ImageView img;
+    BinView bin;
+    geom_layout(P, (char*)geom_buffer, &geom);
+    image_layout(W, H, (char*)img_buffer, &img);
+    bin_layout(capacity, (char*)binning_buffer, &bin);
+    int rc;
+    if (debug) {
+        int32_t cnt[2];
+        if ((rc = check_cuda(cudaMemcpyAsync(cnt, img.counters, sizeof(cnt), cudaMemcpyDeviceToHost, s), "read counters"))) return rc;
+        if ((rc = check_cuda(cudaStreamSynchronize(s), "read counters"))) return rc;
+        if ((int64_t)cnt[0] > capacity) return fail(G4S_ECAPACITY, "g4s_forward_render: num_rendered exceeds capacity");
+    }
+    ScatterArgs sa;
+    sa.P = P; sa.grid_x = gx; sa.capacity = capacity; sa.geom = geom; sa.tile_offset = img.tile_offset;
+    sa.tile_cursor = img.tile_count; sa.keys = bin.keys; sa.counters = img.counters;
+    launch_scatter(sa, s);
+    if ((rc = stage_check(debug, s, "scatter"))) return rc;
+
+    TileSortArgs ts;
+    ts.num_tiles = gx * gy; ts.capacity = capacity; ts.tile_offset = img.tile_offset; ts.tile_order = img.tile_order;
+    ts.keys = bin.keys; ts.list = bin.list; ts.counters = img.counters;
+    launch_tile_sort(ts, s);
+    if ((rc = stage_check(debug, s, "tile_sort"))) return rc;
+
+    BlendFwdArgs ba;
+    ba.W = W; ba.H = H; ba.grid_x = gx; ba.grid_y = gy; ba.capacity = capacity;
+    ba.tile_offset = img.tile_offset; ba.tile_order = img.tile_order; ba.list = bin.list; ba.rec = geom.rec;
+    ba.bg = background; ba.final_T = img.final_T; ba.n_contrib = img.n_contrib;
+    ba.out_color = out_color; ba.out_others = out_others; ba.counters = img.counters;
+    launch_blend_fwd(ba, s);
+    return stage_check(debug, s, "blend_fwd");
+}
+
+int g4s_backward(int P, int D, int M, int W, int H, const float* background, const float* means3D,
+                 const float* shs, const float* colors_precomp, const float* scales, float scale_modifier,
+                 const float* rotations, const float* transMat_precomp, const float* viewmatrix,
+                 const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
+                 const int* radii, const void* geom_buffer, const void* binning_buffer,
+                 const void* img_buffer, const float* dL_dout_color, const float* dL_dout_others,
+                 float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors,
+                 float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dtransMat,
+                 void* scratch, void* stream, int debug) {
+    (void)scale_modifier; (void)colors_precomp; (void)transMat_precomp;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P < 0 || W <= 0 || H <= 0) return fail(G4S_EINVAL, "g4s_backward: bad sizes");
+    if (P == 0) return G4S_OK;
+    if (!geom_buffer || !binning_buffer || !img_buffer || !scratch || !dL_dout_color || !dL_dout_others ||
+        !dL_dmeans3D || !dL_dmeans2D || !dL_dcolors || !dL_dopacity || !dL_dscales || !dL_drotations ||
+        !dL_dtransMat || !radii || !means3D || !background)
+        return fail(G4S_EINVAL, "g4s_backward: null buffer");
+    if (M > 0 && shs && !dL_dsh) return fail(G4S_EINVAL, "g4s_backward: dL_dsh required");
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    GeomView geom;
+    ImageView img;
+    BinView bin;
+    geom_layout(P, (char*)geom_buffer, &geom);
+    image_layout(W, H, (char*)img_buffer, &img);
+    bin_layout(1, (char*)binning_buffer, &bin);  // the sorted list is at offset 0 for every capacity
+    int rc;
+    float4* acc = (float4*)scratch;
+    if ((rc = check_cuda(cudaMemsetAsync(acc, 0, (size_t)P * ACC_FLOATS * sizeof(float), s), "memset acc"))) return rc;
+
+    BlendBwdArgs bb;
+    bb.W = W; bb.H = H; bb.grid_x = gx; bb.grid_y = gy;
+    bb.tile_offset = img.tile_offset; bb.tile_order = img.tile_order;
+    bb.list = bin.list;
+    bb.rec = geom.rec; bb.bg = background; bb.final_T = img.final_T; bb.n_contrib = img.n_contrib;
+    bb.dL_dpix = dL_dout_color; bb.dL_dothers = dL_dout_others; bb.acc = acc;
+    launch_blend_bwd(bb, s);
+    if ((rc = stage_check(debug, s, "blend_bwd"))) return rc;
+
+    ProjectBwdArgs pb;
+    pb.P = P; pb.D = D; pb.M = M; pb.means3D = means3D; pb.shs = shs; pb.scales = scales; pb.rotations = rotations;
+    pb.view = viewmatrix; pb.proj = projmatrix; pb.campos = cam_pos;
+    pb.focal_y = H / (2.0f * tan_fovy);
+    pb.focal_x = W / (2.0f * tan_fovx);
+    pb.tan_fovx = tan_fovx; pb.tan_fovy = tan_fovy; pb.radii = radii; pb.geom = geom; pb.acc = acc;
+    pb.dL_dmeans3D = dL_dmeans3D; pb.dL_dmeans2D = dL_dmeans2D; pb.dL_dsh = (M > 0 && shs) ? dL_dsh : nullptr;
+    pb.dL_dcolors = dL_dcolors; pb.dL_dopacity = dL_dopacity; pb.dL_dscales = dL_dscales; pb.dL_drots = dL_drotations;
+    pb.dL_dtransMat = dL_dtransMat;
+    launch_project_bwd(pb, s);
+    return stage_check(debug, s, "project_bwd");
+}
+
+int g4s_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream) {
+    (void)projmatrix;
+    if (P < 0) return fail(G4S_EINVAL, "g4s_mark_visible: bad P");
+    if (P == 0) return G4S_OK;
+    if (!means3D || !viewmatrix || !present) return fail(G4S_EINVAL, "g4s_mark_visible: null buffer");
+    launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+    return stage_check(false, (cudaStream_t)stream, "mark_visible");
+}
+
+// ---- introspection ---------------------------------------------------------------------------
+namespace g4s {
+__global__ void decode_geom_kernel(int P, GeomView geom, float* transMat, float* means2D, float* normal_opacity,
+                                   float* rgb, float* depths, float* bbox, uint8_t* clamped, uint32_t* tiles_touched) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float4* r = geom.rec + (size_t)i * REC_F4;
+    const float4 q0 = r[0], q1 = r[1], q2 = r[2], q3 = r[3], q4 = r[4], q5 = r[5];
+    if (transMat) {
+        float* t = transMat + 9 * (size_t)i;
+        t[0] = q1.x; t[1] = q1.y; t[2] = q1.z; t[3] = q1.w; t[4] = q2.x; t[5] = q2.y; t[6] = q2.z; t[7] = q2.w; t[8] = q3.x;
+    }
+    if (means2D) { means2D[2 * i] = q3.y; means2D[2 * i + 1] = q3.z; }
+    if (normal_opacity) { normal_opacity[4 * i] = q4.x; normal_opacity[4 * i + 1] = q4.y; normal_opacity[4 * i + 2] = q4.z; normal_opacity[4 * i + 3] = q3.w; }
+    if (rgb) { rgb[3 * i] = q4.w; rgb[3 * i + 1] = q5.x; rgb[3 * i + 2] = q5.y; }
+    if (depths) depths[i] = geom.depth[i];
+    if (bbox) { bbox[4 * i] = q0.x; bbox[4 * i + 1] = q0.y; bbox[4 * i + 2] = q0.z; bbox[4 * i + 3] = q0.w; }
+    if (clamped) { const uint8_t m = geom.clamped[i]; clamped[3 * i] = m & 1; clamped[3 * i + 1] = (m >> 1) & 1; clamped[3 * i + 2] = (m >> 2) & 1; }
+    if (tiles_touched) tiles_touched[i] = geom.ntiles[i];
+}
+__global__ void decode_ranges_kernel(int T, const uint32_t* tile_offset, uint32_t* ranges) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T) return;
+    ranges[2 * i] = tile_offset[i];
+    ranges[2 * i + 1] = tile_offset[i + 1];
+}
+}  // namespace g4s
+
+int g4s_debug_decode_geom(int P, const void* geom_buffer, float* transMat, float* means2D, float* normal_opacity,
+                          float* rgb, float* depths, float* bbox, uint8_t* clamped, uint32_t* tiles_touched, void* stream) {
+    if (P <= 0) return G4S_OK;
+    GeomView geom;
+    geom_layout(P, (char*)geom_buffer, &geom);
+    decode_geom_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P, geom, transMat, means2D, normal_opacity, rgb,
+                                                                          depths, bbox, clamped, tiles_touched);
+    return stage_check(false, (cudaStream_t)stream, "decode_geom");
+}
+
+int g4s_debug_decode_lists(int W, int H, const void* img_buffer, const void* binning_buffer, int64_t capacity,
+                           uint32_t* ranges, float* final_T, uint32_t* n_contrib, uint32_t* point_list, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    ImageView img;
+    BinView bin;
+    image_layout(W, H, (char*)img_buffer, &img);
+    bin_layout(capacity, (char*)binning_buffer, &bin);
+    const int T = ((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+    const size_t N = (size_t)W * H;
+    int rc;
+    if (ranges) decode_ranges_kernel<<<(T + 255) / 256, 256, 0, s>>>(T, img.tile_offset, ranges);
+    if (final_T && (rc = check_cuda(cudaMemcpyAsync(final_T, img.final_T, 3 * N * sizeof(float), cudaMemcpyDeviceToDevice, s), "copy final_T"))) return rc;
+    if (n_contrib && (rc = check_cuda(cudaMemcpyAsync(n_contrib, img.n_contrib, 2 * N * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s), "copy n_contrib"))) return rc;
+    if (point_list && binning_buffer && capacity > 0 &&
+        (rc = check_cuda(cudaMemcpyAsync(point_list, bin.list, (size_t)capacity * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s), "copy list"))) return rc;
+    return stage_check(false, s, "decode_lists");
+}
+
+}  // extern "C"

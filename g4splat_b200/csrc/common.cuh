@@ -1,0 +1,180 @@
+// common.cuh -- shared constants, buffer layouts and small device helpers of the B200 surfel
+// rasterizer.  Semantics follow the reference (RAST = 2d-gaussian-splatting/submodules/
+// diff-surfel-rasterization, CR = RAST/cuda_rasterizer); code and data layout are our own.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace g4s {
+
+// ---- constants of the spec (CR/config.h:14-16, CR/auxiliary.h:21-39) -------------------------
+constexpr int TILE = 16;                 // binning tile edge in pixels (BLOCK_X = BLOCK_Y = 16)
+constexpr int TILE_PIX = TILE * TILE;    // 256 pixels = 8 warps
+constexpr int REGION_W = 8;              // a warp owns an 8x4 pixel region of the tile
+constexpr int REGION_H = 4;
+constexpr float NEAR_N = 0.2f;           // near_n
+constexpr float FAR_N = 100.0f;          // far_n
+constexpr float FILTER_INV_SQUARE = 2.0f;
+constexpr float ALPHA_MIN = 1.0f / 255.0f;
+constexpr float ALPHA_MAX = 0.99f;
+constexpr float T_MIN = 0.0001f;
+
+// ---- projected record: 6 x float4 = 96 B per Gaussian -----------------------------------------
+// q0 = contribution bbox in pixels (xmin, ymin, xmax, ymax): pixels outside can never reach
+//      alpha >= 1/255 for this Gaussian (exact culling, see project.cu)
+// q1 = (Tu.x, Tu.y, Tu.z, Tv.x)   q2 = (Tv.y, Tv.z, Tw.x, Tw.y)   q3 = (Tw.z, cx, cy, opacity)
+// q4 = (nx, ny, nz, r)            q5 = (g, b, depth, 0)
+constexpr int REC_F4 = 6;
+constexpr int REC_FLOATS = REC_F4 * 4;
+
+// ---- blend-stage gradient accumulator: 5 x float4 = 80 B per Gaussian -------------------------
+// a0 = dT[0..3]  a1 = dT[4..7]  a2 = (dT[8], dmean2D.x, dmean2D.y, dopacity)
+// a3 = (dcolor.r, dcolor.g, dcolor.b, dnormal.x)   a4 = (dnormal.y, dnormal.z, 0, 0)
+constexpr int ACC_F4 = 5;
+constexpr int ACC_FLOATS = ACC_F4 * 4;
+
+// ---- counters (device int32[8] inside the image buffer) ---------------------------------------
+enum { CNT_RENDERED = 0, CNT_MAXLEN = 1, CNT_VISIBLE = 2, CNT_PREFILTER_VIOLATION = 3, CNT_N = 8 };
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Geometry buffer (per Gaussian).  All sections 256-byte aligned.
+struct GeomView {
+    float4* rec;        // [P][6]
+    float* depth;       // [P]
+    uint32_t* ntiles;   // [P] tiles touched after exact culling
+    ushort4* rect;      // [P] culled tile rectangle (x0, y0, x1, y1), x1/y1 exclusive
+    uint8_t* clamped;   // [P] bit c set when SH colour channel c was clamped at 0
+};
+__host__ __device__ inline size_t geom_layout(int P, char* base, GeomView* v) {
+    size_t off = 0;
+    size_t n = (size_t)(P > 0 ? P : 1);
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    size_t o_rec = take(n * REC_FLOATS * sizeof(float));
+    size_t o_depth = take(n * sizeof(float));
+    size_t o_nt = take(n * sizeof(uint32_t));
+    size_t o_rect = take(n * sizeof(ushort4));
+    size_t o_cl = take(n);
+    if (v) {
+        v->rec = (float4*)(base + o_rec);
+        v->depth = (float*)(base + o_depth);
+        v->ntiles = (uint32_t*)(base + o_nt);
+        v->rect = (ushort4*)(base + o_rect);
+        v->clamped = (uint8_t*)(base + o_cl);
+    }
+    return off;
+}
+
+// Image buffer (per pixel + per tile).
+struct ImageView {
+    float* final_T;         // [3][N]: T, M1, M2
+    uint32_t* n_contrib;    // [2][N]: last contributor, median contributor (1-based list pos)
+    uint32_t* tile_count;   // [T]  instances per tile (plan); reused as scatter cursor
+    uint32_t* tile_offset;  // [T+1] exclusive scan
+    uint32_t* tile_order;   // [T]  tile ids, longest list first (blend launch order)
+    int32_t* counters;      // [CNT_N]
+};
+__host__ __device__ inline size_t image_layout(int W, int H, char* base, ImageView* v) {
+    size_t N = (size_t)W * H;
+    size_t T = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    size_t o_ft = take(3 * N * sizeof(float));
+    size_t o_nc = take(2 * N * sizeof(uint32_t));
+    size_t o_tc = take(T * sizeof(uint32_t));
+    size_t o_to = take((T + 1) * sizeof(uint32_t));
+    size_t o_ord = take(T * sizeof(uint32_t));
+    size_t o_cnt = take(CNT_N * sizeof(int32_t));
+    if (v) {
+        v->final_T = (float*)(base + o_ft);
+        v->n_contrib = (uint32_t*)(base + o_nc);
+        v->tile_count = (uint32_t*)(base + o_tc);
+        v->tile_offset = (uint32_t*)(base + o_to);
+        v->tile_order = (uint32_t*)(base + o_ord);
+        v->counters = (int32_t*)(base + o_cnt);
+    }
+    return off;
+}
+
+// Binning buffer (per instance).
+struct BinView {
+    unsigned long long* keys;  // [cap]  depth_bits << 32 | gaussian, bucketed by tile, unsorted
+    uint32_t* list;            // [cap]  gaussian ids, per tile sorted by (depth, id)
+};
+__host__ __device__ inline size_t bin_layout(int64_t cap, char* base, BinView* v) {
+    size_t n = (size_t)(cap > 0 ? cap : 1);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    // the list comes first so that its address does not depend on the capacity (the backward
+    // only needs the list and is not told the capacity)
+    size_t o_l = take(n * sizeof(uint32_t));
+    size_t o_k = take(n * sizeof(unsigned long long));
+    if (v) {
+        v->keys = (unsigned long long*)(base + o_k);
+        v->list = (uint32_t*)(base + o_l);
+    }
+    return off;
+}
+
+// ---- tiny vector helpers (componentwise, evaluation order spelled out) ------------------------
+struct f3 { float x, y, z; };
+__device__ __forceinline__ f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ f3 mul3(f3 a, f3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ f3 scale3(float s, f3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ f3 sub3(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float sum3(f3 a) { return a.x + a.y + a.z; }
+__device__ __forceinline__ f3 cross3(f3 a, f3 b) {
+    return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+
+// view/projection matrices are 16 floats, memory = column-major of the column-vector matrix
+// (CR/auxiliary.h:78-121)
+__device__ __forceinline__ f3 xform_point_4x3(f3 p, const float* m) {
+    return mk3(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12],
+               m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+               m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14]);
+}
+__device__ __forceinline__ f3 xform_vec_4x3(f3 p, const float* m) {
+    return mk3(m[0] * p.x + m[4] * p.y + m[8] * p.z,
+               m[1] * p.x + m[5] * p.y + m[9] * p.z,
+               m[2] * p.x + m[6] * p.y + m[10] * p.z);
+}
+__device__ __forceinline__ f3 xform_vec_4x3_T(f3 p, const float* m) {
+    return mk3(m[0] * p.x + m[1] * p.y + m[2] * p.z,
+               m[4] * p.x + m[5] * p.y + m[6] * p.z,
+               m[8] * p.x + m[9] * p.y + m[10] * p.z);
+}
+
+// Rotation matrix of a (w,x,y,z) quaternion, normalised with rsqrtf like the reference
+// (CR/auxiliary.h:212-234).  R[c] = column c.
+__device__ __forceinline__ void quat_to_R(float4 q /* x=w y=x z=y w=z */, f3 R[3]) {
+    float s = rsqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+    float w = q.x * s, x = q.y * s, y = q.z * s, z = q.w * s;
+    R[0] = mk3(1.f - 2.f * (y * y + z * z), 2.f * (x * y + w * z), 2.f * (x * z - w * y));
+    R[1] = mk3(2.f * (x * y - w * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z + w * x));
+    R[2] = mk3(2.f * (x * z + w * y), 2.f * (y * z - w * x), 1.f - 2.f * (x * x + y * y));
+}
+
+// Tangent-plane -> pixel homography T = (Tu, Tv, Tw) (CR/forward.cu:75-115, glm evaluation order):
+//   X[c][r] = sum_j S[r][j] * proj[c + 4j]  with S[0] = (sx*R0, 0), S[1] = (sy*R1, 0), S[2] = (p, 1)
+//   Tu[r] = X[0][r]*W/2 + X[3][r]*(W-1)/2 ; Tv[r] = X[1][r]*H/2 + X[3][r]*(H-1)/2 ; Tw[r] = X[3][r]
+// The zero entries of splat2world / ndc2pix contribute exact zeros and are left out.
+__device__ __forceinline__ void build_T(f3 p, float sx, float sy, const f3 R[3], const float* pm,
+                                        int W, int H, f3& Tu, f3& Tv, f3& Tw) {
+    f3 L0 = mk3(R[0].x * sx, R[0].y * sx, R[0].z * sx);
+    f3 L1 = mk3(R[1].x * sy, R[1].y * sy, R[1].z * sy);
+    float X[4][3];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        X[c][0] = L0.x * pm[c] + L0.y * pm[c + 4] + L0.z * pm[c + 8];
+        X[c][1] = L1.x * pm[c] + L1.y * pm[c + 4] + L1.z * pm[c + 8];
+        X[c][2] = p.x * pm[c] + p.y * pm[c + 4] + p.z * pm[c + 8] + pm[c + 12];
+    }
+    const float hw = float(W) / 2.0f, hw1 = float(W - 1) / 2.0f;
+    const float hh = float(H) / 2.0f, hh1 = float(H - 1) / 2.0f;
+    Tu = mk3(X[0][0] * hw + X[3][0] * hw1, X[0][1] * hw + X[3][1] * hw1, X[0][2] * hw + X[3][2] * hw1);
+    Tv = mk3(X[1][0] * hh + X[3][0] * hh1, X[1][1] * hh + X[3][1] * hh1, X[1][2] * hh + X[3][2] * hh1);
+    Tw = mk3(X[3][0], X[3][1], X[3][2]);
+}
+
+}  // namespace g4s

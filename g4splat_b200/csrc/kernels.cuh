@@ -1,0 +1,98 @@
+// kernels.cuh -- argument blocks and launchers shared between the translation units.
+#pragma once
+#include "common.cuh"
+
+namespace g4s {
+
+void count_launch();  // bumps the process-wide launch counter (api.cu)
+
+struct ProjectArgs {
+    int P, D, M, W, H, grid_x, grid_y, prefiltered;
+    const float* means3D; const float* shs; const float* colors_precomp; const float* opacities;
+    const float* scales; float scale_modifier; const float* rotations; const float* transMat_precomp;
+    const float* view; const float* proj; const float* campos;
+    int* radii;
+    GeomView geom;
+    uint32_t* tile_count;
+    int32_t* counters;
+};
+void launch_project_fwd(const ProjectArgs& a, cudaStream_t s);
+
+struct TileScanArgs {
+    int num_tiles;
+    uint32_t* tile_count;   // in: counts; out: zeroed (becomes the scatter cursor)
+    uint32_t* tile_offset;  // [T+1]
+    uint32_t* tile_order;   // [T] longest list first
+    int32_t* counters;
+};
+void launch_tile_scan(const TileScanArgs& a, cudaStream_t s);
+
+struct ScatterArgs {
+    int P, grid_x;
+    int64_t capacity;
+    GeomView geom;
+    const uint32_t* tile_offset;
+    uint32_t* tile_cursor;
+    unsigned long long* keys;
+    const int32_t* counters;
+};
+void launch_scatter(const ScatterArgs& a, cudaStream_t s);
+
+struct TileSortArgs {
+    int num_tiles;
+    int64_t capacity;
+    const uint32_t* tile_offset;
+    const uint32_t* tile_order;
+    unsigned long long* keys;
+    uint32_t* list;
+    const int32_t* counters;
+};
+void launch_tile_sort(const TileSortArgs& a, cudaStream_t s);
+
+struct BlendFwdArgs {
+    int W, H, grid_x, grid_y;
+    int64_t capacity;
+    const uint32_t* tile_offset;
+    const uint32_t* tile_order;
+    const uint32_t* list;
+    const float4* rec;
+    const float* bg;
+    float* final_T;        // [3][N]
+    uint32_t* n_contrib;   // [2][N]
+    float* out_color;      // [3][N]
+    float* out_others;     // [7][N]
+    const int32_t* counters;
+};
+void launch_blend_fwd(const BlendFwdArgs& a, cudaStream_t s);
+
+struct BlendBwdArgs {
+    int W, H, grid_x, grid_y;
+    const uint32_t* tile_offset;
+    const uint32_t* tile_order;
+    const uint32_t* list;
+    const float4* rec;
+    const float* bg;
+    const float* final_T;
+    const uint32_t* n_contrib;
+    const float* dL_dpix;     // [3][N]
+    const float* dL_dothers;  // [7][N]
+    float4* acc;              // [P][5], zeroed by the caller
+};
+void launch_blend_bwd(const BlendBwdArgs& a, cudaStream_t s);
+
+struct ProjectBwdArgs {
+    int P, D, M;
+    const float* means3D; const float* shs; const float* scales; const float* rotations;
+    const float* view; const float* proj; const float* campos;
+    float focal_x, focal_y, tan_fovx, tan_fovy;
+    const int* radii;
+    GeomView geom;
+    const float4* acc;
+    float* dL_dmeans3D; float* dL_dmeans2D; float* dL_dsh; float* dL_dcolors; float* dL_dopacity;
+    float* dL_dscales; float* dL_drots; float* dL_dtransMat;
+};
+void launch_project_bwd(const ProjectBwdArgs& a, cudaStream_t s);
+
+void launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s);
+
+}  // namespace g4s

@@ -1,0 +1,447 @@
+// project.cu -- per-Gaussian stages: forward projection (+ exact tile culling + per-tile counts),
+// instance scatter, backward projection, markVisible.
+//
+// Reference semantics restated from (CR = RAST/cuda_rasterizer):
+//   forward   CR/forward.cu:150-253 preprocessCUDA, :75-115 compute_transmat, :119-147 compute_aabb,
+//             :20-71 computeColorFromSH, CR/auxiliary.h:66-76 getRect, :184-209 in_frustum
+//   scatter   CR/rasterizer_impl.cu:70-111 duplicateWithKeys
+//   backward  CR/backward.cu:586-641 preprocessCUDA, :443-584 compute_transmat_aabb, :20-139 SH
+//   visible   CR/rasterizer_impl.cu:54-66 checkFrustum
+// What is different by design: the tile set of a Gaussian is the reference rectangle intersected
+// with the bounding box of the pixels that can reach alpha >= 1/255 ("contribution bbox"), so
+// the per-tile lists only hold instances that can change a pixel; per-tile counts are
+// accumulated here, so no prefix sum over Gaussians and no global 64-bit sort is needed.
+#include "kernels.cuh"
+
+namespace g4s {
+
+// SH basis constants (CR/auxiliary.h:42-59)
+__device__ const float SH_C0 = 0.28209479177387814f;
+__device__ const float SH_C1 = 0.4886025119029199f;
+__device__ const float SH_C2[] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                  -1.0925484305920792f, 0.5462742152960396f};
+__device__ const float SH_C3[] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                  0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
+                                  -0.5900435899266435f};
+
+// Degree-D real SH -> RGB for one Gaussian, + 0.5, clamp at 0 (CR/forward.cu:20-71).
+__device__ __forceinline__ f3 sh_to_rgb(int deg, const float* __restrict__ sh /* [M][3] */, f3 dir,
+                                        uint8_t& clamp_mask) {
+    auto c = [&](int k) { return mk3(sh[3 * k], sh[3 * k + 1], sh[3 * k + 2]); };
+    f3 r = scale3(SH_C0, c(0));
+    if (deg > 0) {
+        const float x = dir.x, y = dir.y, z = dir.z;
+        f3 a = c(1), b = c(2), d = c(3);
+        const float c1y = SH_C1 * y, c1z = SH_C1 * z, c1x = SH_C1 * x;
+        r = mk3(r.x - c1y * a.x + c1z * b.x - c1x * d.x, r.y - c1y * a.y + c1z * b.y - c1x * d.y,
+                r.z - c1y * a.z + c1z * b.z - c1x * d.z);
+        if (deg > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            const float k4 = SH_C2[0] * xy, k5 = SH_C2[1] * yz, k6 = SH_C2[2] * (2.0f * zz - xx - yy),
+                        k7 = SH_C2[3] * xz, k8 = SH_C2[4] * (xx - yy);
+            f3 s4 = c(4), s5 = c(5), s6 = c(6), s7 = c(7), s8 = c(8);
+            r = mk3(r.x + k4 * s4.x + k5 * s5.x + k6 * s6.x + k7 * s7.x + k8 * s8.x,
+                    r.y + k4 * s4.y + k5 * s5.y + k6 * s6.y + k7 * s7.y + k8 * s8.y,
+                    r.z + k4 * s4.z + k5 * s5.z + k6 * s6.z + k7 * s7.z + k8 * s8.z);
+            if (deg > 2) {
+                const float k9 = SH_C3[0] * y * (3.0f * xx - yy), k10 = SH_C3[1] * xy * z,
+                            k11 = SH_C3[2] * y * (4.0f * zz - xx - yy),
+                            k12 = SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy),
+                            k13 = SH_C3[4] * x * (4.0f * zz - xx - yy), k14 = SH_C3[5] * z * (xx - yy),
+                            k15 = SH_C3[6] * x * (xx - 3.0f * yy);
+                f3 s9 = c(9), s10 = c(10), s11 = c(11), s12 = c(12), s13 = c(13), s14 = c(14), s15 = c(15);
+                r = mk3(r.x + k9 * s9.x + k10 * s10.x + k11 * s11.x + k12 * s12.x + k13 * s13.x + k14 * s14.x + k15 * s15.x,
+                        r.y + k9 * s9.y + k10 * s10.y + k11 * s11.y + k12 * s12.y + k13 * s13.y + k14 * s14.y + k15 * s15.y,
+                        r.z + k9 * s9.z + k10 * s10.z + k11 * s11.z + k12 * s12.z + k13 * s13.z + k14 * s14.z + k15 * s15.z);
+            }
+        }
+    }
+    r = mk3(r.x + 0.5f, r.y + 0.5f, r.z + 0.5f);
+    clamp_mask = (uint8_t)((r.x < 0 ? 1 : 0) | (r.y < 0 ? 2 : 0) | (r.z < 0 ? 4 : 0));
+    return mk3(fmaxf(r.x, 0.0f), fmaxf(r.y, 0.0f), fmaxf(r.z, 0.0f));
+}
+
+// Bounding box (in pixels, inclusive, already padded) of every pixel for which this Gaussian can
+// reach alpha >= 1/255, i.e. min(rho3d, rho2d) <= rho_cut with rho_cut = 2 ln(255 opacity) padded.
+//   rho2d <= rho_cut : disc of radius sqrt(rho_cut / 2) around the low-pass centre (cx, cy)
+//   rho3d <= rho_cut : image of the tangent-plane disc u^2 + v^2 <= rho_cut under the homography
+//                      T; its axis-aligned extent has the closed form of CR/forward.cu:119-147
+//                      with cutoff^2 = rho_cut.  Evaluated in coordinates shifted to (cx, cy) so
+//                      that the centre^2 - second-moment cancellation stays small.
+// Returns false when the Gaussian can never contribute (opacity < 1/255).
+__device__ __forceinline__ bool contribution_bbox(f3 Tu, f3 Tv, f3 Tw, float cx, float cy, float opacity,
+                                                  float4& bb) {
+    if (!(opacity >= ALPHA_MIN)) return false;  // alpha <= opacity < 1/255 for every pixel
+    const float rho_cut = 2.0f * logf(255.0f * opacity) * 1.001f + 1e-3f;
+    const float big = 1e30f;
+    // low-pass disc
+    const float rr = sqrtf(0.5f * rho_cut);
+    float x0 = -rr, x1 = rr, y0 = -rr, y1 = rr;
+    // projected tangent disc, shifted frame: Tu' = Tu - cx Tw, Tv' = Tv - cy Tw
+    const f3 U = mk3(Tu.x - cx * Tw.x, Tu.y - cx * Tw.y, Tu.z - cx * Tw.z);
+    const f3 V = mk3(Tv.x - cy * Tw.x, Tv.y - cy * Tw.y, Tv.z - cy * Tw.z);
+    const float d = rho_cut * (Tw.x * Tw.x + Tw.y * Tw.y) - Tw.z * Tw.z;
+    bool bounded = false;
+    if (d < 0.0f) {  // the disc does not reach the camera plane: its image is an ellipse
+        const float fxy = rho_cut / d, fz = -1.0f / d;
+        const float mx = fxy * (U.x * Tw.x + U.y * Tw.y) + fz * U.z * Tw.z;
+        const float my = fxy * (V.x * Tw.x + V.y * Tw.y) + fz * V.z * Tw.z;
+        const float hx = mx * mx - (fxy * (U.x * U.x + U.y * U.y) + fz * U.z * U.z);
+        const float hy = my * my - (fxy * (V.x * V.x + V.y * V.y) + fz * V.z * V.z);
+        if (hx >= 0.0f && hy >= 0.0f && hx < 1e12f && hy < 1e12f) {
+            const float ex = sqrtf(hx) * 1.0005f, ey = sqrtf(hy) * 1.0005f;
+            x0 = fminf(x0, mx - ex); x1 = fmaxf(x1, mx + ex);
+            y0 = fminf(y0, my - ey); y1 = fmaxf(y1, my + ey);
+            bounded = true;
+        }
+    }
+    if (!bounded) { bb = make_float4(-big, -big, big, big); return true; }
+    const float pad = 0.02f + 2e-6f * (fabsf(cx) + fabsf(cy));
+    bb = make_float4(cx + x0 - pad, cy + y0 - pad, cx + x1 + pad, cy + y1 + pad);
+    if (!(bb.x == bb.x && bb.y == bb.y && bb.z == bb.z && bb.w == bb.w)) bb = make_float4(-big, -big, big, big);
+    return true;
+}
+
+__global__ void __launch_bounds__(256) project_fwd_kernel(ProjectArgs a) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.P) return;
+    a.radii[idx] = 0;
+    a.geom.ntiles[idx] = 0;
+
+    const f3 p = mk3(a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]);
+    const f3 pv = xform_point_4x3(p, a.view);
+    if (pv.z <= 0.2f) {  // in_frustum (CR/auxiliary.h:199)
+        if (a.prefiltered) atomicAdd(&a.counters[CNT_PREFILTER_VIOLATION], 1);
+        return;
+    }
+    f3 Tu, Tv, Tw, normal;
+    if (a.transMat_precomp == nullptr) {
+        const float2 sc = ((const float2*)a.scales)[idx];
+        const float4 q = ((const float4*)a.rotations)[idx];
+        f3 R[3];
+        quat_to_R(q, R);
+        build_T(p, a.scale_modifier * sc.x, a.scale_modifier * sc.y, R, a.proj, a.W, a.H, Tu, Tv, Tw);
+        normal = xform_vec_4x3(R[2], a.view);
+    } else {
+        const float* t = a.transMat_precomp + 9 * (size_t)idx;
+        Tu = mk3(t[0], t[1], t[2]); Tv = mk3(t[3], t[4], t[5]); Tw = mk3(t[6], t[7], t[8]);
+        normal = mk3(0.0f, 0.0f, 1.0f);
+    }
+    // dual-visible flip (CR/forward.cu:211-216)
+    const float cosv = -sum3(mul3(pv, normal));
+    if (cosv == 0) return;
+    const float mult = cosv > 0 ? 1.0f : -1.0f;
+    normal = scale3(mult, normal);
+
+    // 3-sigma AABB: centre + radius exactly as the reference (CR/forward.cu:119-147, :222-233)
+    const f3 tp = mk3(9.0f, 9.0f, -1.0f);
+    const float dist = sum3(mul3(mul3(Tw, Tw), tp));
+    const f3 f = scale3(1 / dist, tp);
+    if (dist == 0.0f) return;
+    const float cx = sum3(mul3(mul3(f, Tu), Tw));
+    const float cy = sum3(mul3(mul3(f, Tv), Tw));
+    const float t0 = sum3(mul3(mul3(f, Tu), Tu));
+    const float t1 = sum3(mul3(mul3(f, Tv), Tv));
+    const float ex = sqrtf(fmaxf(1e-4f, cx * cx - t0));
+    const float ey = sqrtf(fmaxf(1e-4f, cy * cy - t1));
+    const float radius = ceilf(fmaxf(ex, ey));
+
+    // getRect (CR/auxiliary.h:66-76)
+    const int max_radius = (int)radius;
+    const int gx = a.grid_x, gy = a.grid_y;
+    int rx0 = min(gx, max(0, (int)((cx - max_radius) / TILE)));
+    int ry0 = min(gy, max(0, (int)((cy - max_radius) / TILE)));
+    int rx1 = min(gx, max(0, (int)((cx + max_radius + TILE - 1) / TILE)));
+    int ry1 = min(gy, max(0, (int)((cy + max_radius + TILE - 1) / TILE)));
+    if ((rx1 - rx0) * (ry1 - ry0) == 0) return;
+
+    // colour
+    f3 rgb;
+    uint8_t clamp_mask = 0;
+    if (a.colors_precomp == nullptr) {
+        f3 dir = sub3(p, mk3(a.campos[0], a.campos[1], a.campos[2]));
+        const float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
+        dir = mk3(dir.x / len, dir.y / len, dir.z / len);
+        rgb = sh_to_rgb(a.D, a.shs + (size_t)idx * a.M * 3, dir, clamp_mask);
+    } else {
+        rgb = mk3(a.colors_precomp[3 * idx], a.colors_precomp[3 * idx + 1], a.colors_precomp[3 * idx + 2]);
+    }
+    const float opacity = a.opacities[idx];
+
+    // exact culling: tiles of the reference rectangle that hold at least one pixel of the
+    // contribution bbox
+    float4 bb;
+    int nt = 0;
+    const bool can_contribute = contribution_bbox(Tu, Tv, Tw, cx, cy, opacity, bb);
+    if (can_contribute) {
+        // tile t covers pixels [16 t, 16 t + 15]
+        const float fx0 = fmaxf(ceilf((bb.x - (TILE - 1)) / TILE), (float)rx0);
+        const float fy0 = fmaxf(ceilf((bb.y - (TILE - 1)) / TILE), (float)ry0);
+        const float fx1 = fminf(floorf(bb.z / TILE) + 1.0f, (float)rx1);
+        const float fy1 = fminf(floorf(bb.w / TILE) + 1.0f, (float)ry1);
+        rx0 = (int)fx0; ry0 = (int)fy0; rx1 = (int)fx1; ry1 = (int)fy1;
+        if (rx1 > rx0 && ry1 > ry0) nt = (rx1 - rx0) * (ry1 - ry0);
+    }
+    if (nt == 0) { rx0 = ry0 = rx1 = ry1 = 0; bb = make_float4(1e30f, 1e30f, -1e30f, -1e30f); }
+
+    a.radii[idx] = max_radius;
+    float4* rec = a.geom.rec + (size_t)idx * REC_F4;
+    rec[0] = bb;
+    rec[1] = make_float4(Tu.x, Tu.y, Tu.z, Tv.x);
+    rec[2] = make_float4(Tv.y, Tv.z, Tw.x, Tw.y);
+    rec[3] = make_float4(Tw.z, cx, cy, opacity);
+    rec[4] = make_float4(normal.x, normal.y, normal.z, rgb.x);
+    rec[5] = make_float4(rgb.y, rgb.z, pv.z, 0.0f);
+    a.geom.depth[idx] = pv.z;
+    a.geom.clamped[idx] = clamp_mask;
+    a.geom.ntiles[idx] = (uint32_t)nt;
+    a.geom.rect[idx] = make_ushort4((unsigned short)rx0, (unsigned short)ry0, (unsigned short)rx1, (unsigned short)ry1);
+    atomicAdd(&a.counters[CNT_VISIBLE], 1);
+    for (int y = ry0; y < ry1; y++)
+        for (int x = rx0; x < rx1; x++) atomicAdd(&a.tile_count[y * gx + x], 1u);
+}
+
+// One (Gaussian, tile) instance per surviving tile: key = depth bits << 32 | Gaussian id, written
+// to an arbitrary free slot of the tile's bucket; the per-tile sort orders the bucket afterwards.
+__global__ void __launch_bounds__(256) scatter_kernel(ScatterArgs a) {
+    if ((int64_t)a.counters[CNT_RENDERED] > a.capacity) return;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.P) return;
+    if (a.geom.ntiles[idx] == 0) return;
+    const ushort4 r = a.geom.rect[idx];
+    const unsigned long long key_hi = ((unsigned long long)__float_as_uint(a.geom.depth[idx])) << 32;
+    const unsigned long long key = key_hi | (unsigned long long)(uint32_t)idx;
+    for (int y = r.y; y < r.w; y++)
+        for (int x = r.x; x < r.z; x++) {
+            const int t = y * a.grid_x + x;
+            const uint32_t slot = a.tile_offset[t] + atomicAdd(&a.tile_cursor[t], 1u);
+            a.keys[slot] = key;
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward of the SH colour (CR/backward.cu:20-139): writes dL_dsh[idx][k] for k < (D+1)^2 and
+// zeros above, returns the view-direction term to add to dL_dmean3D.
+__device__ __forceinline__ f3 sh_backward(int deg, int M, const float* __restrict__ sh, f3 dir_orig,
+                                          uint8_t clamp_mask, f3 dL_dcolor, float* __restrict__ dsh) {
+    const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
+    const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
+    f3 g = mk3(dL_dcolor.x * ((clamp_mask & 1) ? 0.f : 1.f), dL_dcolor.y * ((clamp_mask & 2) ? 0.f : 1.f),
+               dL_dcolor.z * ((clamp_mask & 4) ? 0.f : 1.f));
+    auto c = [&](int k) { return mk3(sh[3 * k], sh[3 * k + 1], sh[3 * k + 2]); };
+    auto put = [&](int k, float v) { dsh[3 * k] = v * g.x; dsh[3 * k + 1] = v * g.y; dsh[3 * k + 2] = v * g.z; };
+    auto axpy = [&](f3& acc, float s, f3 v) { acc.x += s * v.x; acc.y += s * v.y; acc.z += s * v.z; };
+    f3 dx = mk3(0, 0, 0), dy = mk3(0, 0, 0), dz = mk3(0, 0, 0);
+    put(0, SH_C0);
+    int used = 1;
+    if (deg > 0) {
+        put(1, -SH_C1 * y); put(2, SH_C1 * z); put(3, -SH_C1 * x);
+        dx = scale3(-SH_C1, c(3)); dy = scale3(-SH_C1, c(1)); dz = scale3(SH_C1, c(2));
+        used = 4;
+        if (deg > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            put(4, SH_C2[0] * xy); put(5, SH_C2[1] * yz); put(6, SH_C2[2] * (2.f * zz - xx - yy));
+            put(7, SH_C2[3] * xz); put(8, SH_C2[4] * (xx - yy));
+            axpy(dx, SH_C2[0] * y, c(4)); axpy(dx, SH_C2[2] * 2.f * -x, c(6)); axpy(dx, SH_C2[3] * z, c(7)); axpy(dx, SH_C2[4] * 2.f * x, c(8));
+            axpy(dy, SH_C2[0] * x, c(4)); axpy(dy, SH_C2[1] * z, c(5)); axpy(dy, SH_C2[2] * 2.f * -y, c(6)); axpy(dy, SH_C2[4] * 2.f * -y, c(8));
+            axpy(dz, SH_C2[1] * y, c(5)); axpy(dz, SH_C2[2] * 2.f * 2.f * z, c(6)); axpy(dz, SH_C2[3] * x, c(7));
+            used = 9;
+            if (deg > 2) {
+                put(9, SH_C3[0] * y * (3.f * xx - yy)); put(10, SH_C3[1] * xy * z);
+                put(11, SH_C3[2] * y * (4.f * zz - xx - yy)); put(12, SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy));
+                put(13, SH_C3[4] * x * (4.f * zz - xx - yy)); put(14, SH_C3[5] * z * (xx - yy));
+                put(15, SH_C3[6] * x * (xx - 3.f * yy));
+                axpy(dx, SH_C3[0] * 3.f * 2.f * xy, c(9)); axpy(dx, SH_C3[1] * yz, c(10)); axpy(dx, SH_C3[2] * -2.f * xy, c(11));
+                axpy(dx, SH_C3[3] * -3.f * 2.f * xz, c(12)); axpy(dx, SH_C3[4] * (-3.f * xx + 4.f * zz - yy), c(13));
+                axpy(dx, SH_C3[5] * 2.f * xz, c(14)); axpy(dx, SH_C3[6] * 3.f * (xx - yy), c(15));
+                axpy(dy, SH_C3[0] * 3.f * (xx - yy), c(9)); axpy(dy, SH_C3[1] * xz, c(10)); axpy(dy, SH_C3[2] * (-3.f * yy + 4.f * zz - xx), c(11));
+                axpy(dy, SH_C3[3] * -3.f * 2.f * yz, c(12)); axpy(dy, SH_C3[4] * -2.f * xy, c(13));
+                axpy(dy, SH_C3[5] * -2.f * yz, c(14)); axpy(dy, SH_C3[6] * -3.f * 2.f * xy, c(15));
+                axpy(dz, SH_C3[1] * xy, c(10)); axpy(dz, SH_C3[2] * 4.f * 2.f * yz, c(11)); axpy(dz, SH_C3[3] * 3.f * (2.f * zz - xx - yy), c(12));
+                axpy(dz, SH_C3[4] * 4.f * 2.f * xz, c(13)); axpy(dz, SH_C3[5] * (xx - yy), c(14));
+                used = 16;
+            }
+        }
+    }
+    for (int k = used; k < M; k++) { dsh[3 * k] = 0.f; dsh[3 * k + 1] = 0.f; dsh[3 * k + 2] = 0.f; }
+    const f3 ddir = mk3(dx.x * g.x + dx.y * g.y + dx.z * g.z, dy.x * g.x + dy.y * g.y + dy.z * g.z,
+                        dz.x * g.x + dz.y * g.y + dz.z * g.z);
+    // dnormvdv (CR/auxiliary.h:127-137)
+    const f3 v = dir_orig;
+    const float sum2 = v.x * v.x + v.y * v.y + v.z * v.z;
+    const float inv = 1.0f / sqrtf(sum2 * sum2 * sum2);
+    return mk3(((+sum2 - v.x * v.x) * ddir.x - v.y * v.x * ddir.y - v.z * v.x * ddir.z) * inv,
+               (-v.x * v.y * ddir.x + (sum2 - v.y * v.y) * ddir.y - v.z * v.y * ddir.z) * inv,
+               (-v.x * v.z * ddir.x - v.y * v.z * ddir.y + (sum2 - v.z * v.z) * ddir.z) * inv);
+}
+
+// Backward projection: one thread per Gaussian, writes EVERY output element (zeros when the
+// Gaussian was not visible) so the caller never has to clear the gradient tensors.
+__global__ void __launch_bounds__(256) project_bwd_kernel(ProjectBwdArgs a) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.P) return;
+    float* dsh = a.dL_dsh ? a.dL_dsh + (size_t)idx * a.M * 3 : nullptr;
+    const bool visible = a.radii[idx] > 0;
+    if (!visible) {
+        for (int i = 0; i < 3; i++) { a.dL_dmeans3D[3 * idx + i] = 0.f; a.dL_dmeans2D[3 * idx + i] = 0.f; a.dL_dcolors[3 * idx + i] = 0.f; }
+        a.dL_dopacity[idx] = 0.f;
+        a.dL_dscales[2 * idx] = 0.f; a.dL_dscales[2 * idx + 1] = 0.f;
+        for (int i = 0; i < 4; i++) a.dL_drots[4 * idx + i] = 0.f;
+        for (int i = 0; i < 9; i++) a.dL_dtransMat[9 * idx + i] = 0.f;
+        if (dsh) for (int i = 0; i < 3 * a.M; i++) dsh[i] = 0.f;
+        return;
+    }
+    // blend-stage accumulators
+    const float4* acc = a.acc + (size_t)idx * ACC_F4;
+    const float4 a0 = acc[0], a1 = acc[1], a2 = acc[2], a3 = acc[3], a4 = acc[4];
+    float dT[3][3] = {{a0.x, a0.y, a0.z}, {a0.w, a1.x, a1.y}, {a1.z, a1.w, a2.x}};  // dT[j] = d/dT row j (Tu,Tv,Tw)
+    const float blend_dT2 = a0.z, blend_dT5 = a1.y;  // proxy inputs (scales path: untouched accumulators)
+    const float m2x = a2.y, m2y = a2.z;
+    const f3 dcol = mk3(a3.x, a3.y, a3.z);
+    const f3 dnrm = mk3(a3.w, a4.x, a4.y);
+    a.dL_dopacity[idx] = a2.w;
+    a.dL_dcolors[3 * idx] = dcol.x; a.dL_dcolors[3 * idx + 1] = dcol.y; a.dL_dcolors[3 * idx + 2] = dcol.z;
+
+    // W, H as the reference rebuilds them in fp32 (CR/backward.cu:618-619)
+    const int Wq = int(a.focal_x * a.tan_fovx * 2);
+    const int Hq = int(a.focal_y * a.tan_fovy * 2);
+
+    const float4* rec = a.geom.rec + (size_t)idx * REC_F4;
+    const float4 q1 = rec[1], q2 = rec[2], q3 = rec[3];
+    const bool precomp = (a.scales == nullptr);
+    const f3 p = mk3(a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]);
+    f3 Tu, Tv, Tw, R[3], normal = mk3(0, 0, 0);
+    float sx = 0, sy = 0;
+    float Pm[3][4];
+    float4 quat = make_float4(1, 0, 0, 0);
+    if (precomp) {
+        Tu = mk3(q1.x, q1.y, q1.z); Tv = mk3(q1.w, q2.x, q2.y); Tw = mk3(q2.z, q2.w, q3.x);
+    } else {
+        const float2 sc = ((const float2*)a.scales)[idx];
+        quat = ((const float4*)a.rotations)[idx];
+        sx = sc.x; sy = sc.y;  // scale_modifier ignored on purpose (quirk 2, CR/backward.cu:481)
+        quat_to_R(quat, R);
+        // P = world2ndc * ndc2pix (mat3x4), T = transpose(M) * P (CR/backward.cu:490-504)
+        const float nd[3][4] = {{float(Wq) / 2.0f, 0, 0, float(Wq - 1) / 2.0f},
+                                {0, float(Hq) / 2.0f, 0, float(Hq - 1) / 2.0f},
+                                {0, 0, 0, 1}};
+        const float* pm = a.proj;
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                Pm[c][k] = pm[0 + 4 * k] * nd[c][0] + pm[1 + 4 * k] * nd[c][1] + pm[2 + 4 * k] * nd[c][2] + pm[3 + 4 * k] * nd[c][3];
+        const f3 L0 = mk3(R[0].x * sx, R[0].y * sx, R[0].z * sx), L1 = mk3(R[1].x * sy, R[1].y * sy, R[1].z * sy);
+        float Tm[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            Tm[c][0] = L0.x * Pm[c][0] + L0.y * Pm[c][1] + L0.z * Pm[c][2];
+            Tm[c][1] = L1.x * Pm[c][0] + L1.y * Pm[c][1] + L1.z * Pm[c][2];
+            Tm[c][2] = p.x * Pm[c][0] + p.y * Pm[c][1] + p.z * Pm[c][2] + Pm[c][3];
+        }
+        Tu = mk3(Tm[0][0], Tm[0][1], Tm[0][2]); Tv = mk3(Tm[1][0], Tm[1][1], Tm[1][2]); Tw = mk3(Tm[2][0], Tm[2][1], Tm[2][2]);
+        normal = xform_vec_4x3(R[2], a.view);
+    }
+    // low-pass centre gradient -> dT (CR/backward.cu:515-541; cutoff-1 approximation, quirk 4)
+    if (m2x != 0 || m2y != 0) {
+        const float distance = Tw.x * Tw.x + Tw.y * Tw.y - Tw.z * Tw.z;
+        const float f = 1 / distance;
+        const float dpx_dT00 = f * Tw.x, dpx_dT01 = f * Tw.y, dpx_dT02 = -f * Tw.z;
+        const float dpx_dT30 = Tu.x * (f - 2 * f * f * Tw.x * Tw.x);
+        const float dpx_dT31 = Tu.y * (f - 2 * f * f * Tw.y * Tw.y);
+        const float dpx_dT32 = -Tu.z * (f + 2 * f * f * Tw.z * Tw.z);
+        const float dpy_dT30 = Tv.x * (f - 2 * f * f * Tw.x * Tw.x);
+        const float dpy_dT31 = Tv.y * (f - 2 * f * f * Tw.y * Tw.y);
+        const float dpy_dT32 = -Tv.z * (f + 2 * f * f * Tw.z * Tw.z);
+        dT[0][0] += m2x * dpx_dT00; dT[0][1] += m2x * dpx_dT01; dT[0][2] += m2x * dpx_dT02;
+        dT[1][0] += m2y * dpx_dT00; dT[1][1] += m2y * dpx_dT01; dT[1][2] += m2y * dpx_dT02;
+        dT[2][0] += m2x * dpx_dT30 + m2y * dpy_dT30;
+        dT[2][1] += m2x * dpx_dT31 + m2y * dpy_dT31;
+        dT[2][2] += m2x * dpx_dT32 + m2y * dpy_dT32;
+    }
+    float proxy2, proxy5;
+    if (precomp) {
+        // dL_dtransMat is the gradient of the precomputed input and feeds the proxy after the
+        // update above (CR/backward.cu:542-553)
+        for (int j = 0; j < 3; j++) for (int c = 0; c < 3; c++) a.dL_dtransMat[9 * idx + 3 * j + c] = dT[j][c];
+        proxy2 = dT[0][2]; proxy5 = dT[1][2];
+        for (int i = 0; i < 3; i++) a.dL_dmeans3D[3 * idx + i] = 0.f;
+        a.dL_dscales[2 * idx] = 0.f; a.dL_dscales[2 * idx + 1] = 0.f;
+        for (int i = 0; i < 4; i++) a.dL_drots[4 * idx + i] = 0.f;
+    } else {
+        // the reference returns the raw blend-stage accumulator here
+        a.dL_dtransMat[9 * idx + 0] = a0.x; a.dL_dtransMat[9 * idx + 1] = a0.y; a.dL_dtransMat[9 * idx + 2] = a0.z;
+        a.dL_dtransMat[9 * idx + 3] = a0.w; a.dL_dtransMat[9 * idx + 4] = a1.x; a.dL_dtransMat[9 * idx + 5] = a1.y;
+        a.dL_dtransMat[9 * idx + 6] = a1.z; a.dL_dtransMat[9 * idx + 7] = a1.w; a.dL_dtransMat[9 * idx + 8] = a2.x;
+        proxy2 = blend_dT2; proxy5 = blend_dT5;
+        // dL_dM[c][k] = sum_j P[j][k] * dT[j][c]
+        float dM[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) dM[c][k] = Pm[0][k] * dT[0][c] + Pm[1][k] * dT[1][c] + Pm[2][k] * dT[2][c];
+        f3 dtn = xform_vec_4x3_T(dnrm, a.view);
+        const f3 pv = xform_point_4x3(p, a.view);
+        const float cosv = -sum3(mul3(pv, normal));
+        const float mult = cosv > 0 ? 1.0f : -1.0f;
+        dtn = scale3(mult, dtn);
+        // dL_dR columns: dRS0 * sx, dRS1 * sy, dtn ; quat_to_rotmat_vjp (CR/auxiliary.h:237-281)
+        const f3 v0 = mk3(dM[0][0] * sx, dM[0][1] * sx, dM[0][2] * sx);
+        const f3 v1 = mk3(dM[1][0] * sy, dM[1][1] * sy, dM[1][2] * sy);
+        const f3 v2 = dtn;
+        const float s = rsqrtf(quat.w * quat.w + quat.x * quat.x + quat.y * quat.y + quat.z * quat.z);
+        const float w = quat.x * s, x = quat.y * s, y = quat.z * s, z = quat.w * s;
+        // vR[c][r]: v0 = column 0 (x,y,z = rows 0,1,2) ...
+        const float vR01 = v0.y, vR02 = v0.z, vR00 = v0.x, vR10 = v1.x, vR11 = v1.y, vR12 = v1.z, vR20 = v2.x, vR21 = v2.y, vR22 = v2.z;
+        a.dL_drots[4 * idx + 0] = 2.f * (x * (vR12 - vR21) + y * (vR20 - vR02) + z * (vR01 - vR10));
+        a.dL_drots[4 * idx + 1] = 2.f * (-2.f * x * (vR11 + vR22) + y * (vR01 + vR10) + z * (vR02 + vR20) + w * (vR12 - vR21));
+        a.dL_drots[4 * idx + 2] = 2.f * (x * (vR01 + vR10) - 2.f * y * (vR00 + vR22) + z * (vR12 + vR21) + w * (vR20 - vR02));
+        a.dL_drots[4 * idx + 3] = 2.f * (x * (vR02 + vR20) + y * (vR12 + vR21) - 2.f * z * (vR00 + vR11) + w * (vR01 - vR10));
+        a.dL_dscales[2 * idx] = dM[0][0] * R[0].x + dM[0][1] * R[0].y + dM[0][2] * R[0].z;
+        a.dL_dscales[2 * idx + 1] = dM[1][0] * R[1].x + dM[1][1] * R[1].y + dM[1][2] * R[1].z;
+        a.dL_dmeans3D[3 * idx] = dM[2][0]; a.dL_dmeans3D[3 * idx + 1] = dM[2][1]; a.dL_dmeans3D[3 * idx + 2] = dM[2][2];
+    }
+    if (a.shs) {
+        const f3 dir = sub3(p, mk3(a.campos[0], a.campos[1], a.campos[2]));
+        const f3 dmean = sh_backward(a.D, a.M, a.shs + (size_t)idx * a.M * 3, dir, a.geom.clamped[idx], dcol, dsh);
+        a.dL_dmeans3D[3 * idx] += dmean.x; a.dL_dmeans3D[3 * idx + 1] += dmean.y; a.dL_dmeans3D[3 * idx + 2] += dmean.z;
+    }
+    // densification proxy (CR/backward.cu:637-640, quirk 5): depth = forward T[8]
+    const float depth = q3.x;
+    a.dL_dmeans2D[3 * idx + 0] = proxy2 * depth * 0.5f * float(Wq);
+    a.dL_dmeans2D[3 * idx + 1] = proxy5 * depth * 0.5f * float(Hq);
+    a.dL_dmeans2D[3 * idx + 2] = 0.f;
+}
+
+__global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means3D,
+                                                           const float* __restrict__ view, uint8_t* __restrict__ present) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const f3 p = mk3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+    const f3 pv = xform_point_4x3(p, view);
+    present[idx] = !(pv.z <= 0.2f);
+}
+
+// ---- launchers --------------------------------------------------------------------------------
+void launch_project_fwd(const ProjectArgs& a, cudaStream_t s) {
+    if (a.P <= 0) return;
+    project_fwd_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a);
+    count_launch();
+}
+void launch_scatter(const ScatterArgs& a, cudaStream_t s) {
+    if (a.P <= 0) return;
+    scatter_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a);
+    count_launch();
+}
+void launch_project_bwd(const ProjectBwdArgs& a, cudaStream_t s) {
+    if (a.P <= 0) return;
+    project_bwd_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a);
+    count_launch();
+}
+void launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s) {
+    if (P <= 0) return;
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, view, present);
+    count_launch();
+}
+
+}  // namespace g4s

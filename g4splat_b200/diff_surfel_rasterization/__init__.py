@@ -1,0 +1,302 @@
+"""Drop-in operator API of the B200-native surfel rasterizer.
+
+Mirrors the reference operator module one to one
+(RAST/diff_surfel_rasterization/__init__.py: rasterize_gaussians :21-42, _RasterizeGaussians
+:44-156, GaussianRasterizationSettings :158-170, GaussianRasterizer :172-222): same names, same
+argument order and meaning, same return order `(color, radii, allmap)`, same two one-of
+exceptions -- so `gaussian_renderer.render()` (2DGS/gaussian_renderer/__init__.py:14,37-53,
+97-106) runs unchanged once this package is importable as `diff_surfel_rasterization`
+(`g4splat_b200.install()` registers it under that name).
+
+Below the API everything is different: torch only allocates tensors and provides the stream;
+the work is done by hand-written sm_100a kernels reached through the C ABI of
+include/g4s_rasterizer.h via ctypes.  There is no CPU / PyTorch fallback.
+
+Host synchronisation: the reference blocks on a device->host copy of `num_rendered` in the
+middle of every forward (CR/rasterizer_impl.cu:282).  Here the forward is launched end to end
+with a guessed instance capacity; the host then waits only for the small "plan" stage to learn
+the true count (the GPU keeps running the rest meanwhile) and re-issues the render stage in the
+rare case the guess was too small.  G4S_SYNC=none skips even that wait (capacity overflow is
+then reported by the next call).
+"""
+from __future__ import annotations
+
+import os
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+
+_LIB = _lib.load()  # raises if the CUDA library is missing: fail loudly, never fall back
+
+NUM_CHANNELS = 3  # CR/config.h:14
+_OTHERS = 7       # depth, alpha, normal xyz, median depth, distortion (CR/auxiliary.h:23-27)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    """Device pointer, or NULL for None / empty tensors (the reference's optional-arg convention)."""
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if t.numel() and t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+class _CapacityPolicy:
+    """Guess for the number of (Gaussian, tile) instances of the next forward, per device."""
+
+    def __init__(self):
+        self.last = {}
+
+    def guess(self, dev: int, P: int) -> int:
+        prev = self.last.get(dev)
+        if prev is None:
+            return max(1 << 20, 6 * P)
+        return max(1 << 16, int(prev * 1.5) + 65536)
+
+    def observe(self, dev: int, R: int) -> None:
+        self.last[dev] = R
+
+
+_capacity = _CapacityPolicy()
+_pending_overflow = []  # (event, pinned counts, capacity) of G4S_SYNC=none calls not yet checked
+_RING = 256             # pinned count slots; a slot is reused only after _RING further forwards
+_ring = None
+_ring_next = 0
+
+
+def _sync_mode() -> str:
+    return os.environ.get("G4S_SYNC", "plan")
+
+
+def _pinned_counts() -> torch.Tensor:
+    """int32[4] view into a pinned ring (cudaHostAlloc per call would serialise the device)."""
+    global _ring, _ring_next
+    if _ring is None:
+        _ring = torch.zeros((_RING, 4), dtype=torch.int32).pin_memory()
+    slot = _ring[_ring_next]
+    _ring_next = (_ring_next + 1) % _RING
+    if _ring_next == 0 and _pending_overflow:
+        torch.cuda.synchronize()
+        _check_pending()
+    return slot
+
+
+def _check_pending() -> None:
+    still = []
+    for ev, counts, cap in _pending_overflow:
+        if ev.query():
+            if int(counts[0]) > cap:
+                _pending_overflow.clear()
+                raise RuntimeError(
+                    f"g4s rasterizer: a previous G4S_SYNC=none forward needed {int(counts[0])} instances "
+                    f"but was given capacity {cap}; its outputs are invalid")
+        else:
+            still.append((ev, counts, cap))
+    _pending_overflow[:] = still
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                        cov3Ds_precomp, raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales,
+                                     rotations, cov3Ds_precomp, raster_settings)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                cov3Ds_precomp, raster_settings):
+        rs = raster_settings
+        if means3D.dim() != 2 or means3D.size(1) != 3:
+            raise RuntimeError("means3D must have dimensions (num_points, 3)")
+        dev = means3D.device
+        P = int(means3D.size(0))
+        H, W = int(rs.image_height), int(rs.image_width)
+        debug = bool(rs.debug)
+
+        means3D_c = _f32c(means3D, "means3D")
+        sh_c = _f32c(sh, "sh")
+        colors_c = _f32c(colors_precomp, "colors")
+        opac_c = _f32c(opacities, "opacity")
+        scales_c = _f32c(scales, "scales")
+        rots_c = _f32c(rotations, "rotations")
+        cov_c = _f32c(cov3Ds_precomp, "transMat_precomp")
+        bg = _f32c(rs.bg, "background")
+        view = _f32c(rs.viewmatrix, "viewmatrix")
+        proj = _f32c(rs.projmatrix, "projmatrix")
+        campos = _f32c(rs.campos, "campos")
+        M = int(sh_c.size(1)) if sh_c.numel() != 0 else 0
+
+        f32 = dict(dtype=torch.float32, device=dev)
+        num_rendered = 0
+        if P == 0:
+            # reference: kernels skipped, zero images returned (rasterize_points.cu:85-99)
+            color = torch.zeros((NUM_CHANNELS, H, W), **f32)
+            others = torch.zeros((_OTHERS, H, W), **f32)
+            radii = torch.zeros((0,), dtype=torch.int32, device=dev)
+            geom = binning = img = torch.empty((0,), dtype=torch.uint8, device=dev)
+        else:
+            with torch.cuda.device(dev):
+                stream = torch.cuda.current_stream(dev)
+                sp = stream.cuda_stream
+                color = torch.empty((NUM_CHANNELS, H, W), **f32)
+                others = torch.empty((_OTHERS, H, W), **f32)
+                radii = torch.empty((P,), dtype=torch.int32, device=dev)
+                geom = torch.empty((_LIB.g4s_geom_bytes(P),), dtype=torch.uint8, device=dev)
+                img = torch.empty((_LIB.g4s_image_bytes(W, H),), dtype=torch.uint8, device=dev)
+                counts = _pinned_counts()
+                mode = _sync_mode()
+                if mode == "none":
+                    _check_pending()
+                _lib.check(_LIB.g4s_forward_plan(
+                    P, int(rs.sh_degree), M, W, H, _ptr(means3D_c), _ptr(sh_c), _ptr(colors_c),
+                    _ptr(opac_c), _ptr(scales_c), float(rs.scale_modifier), _ptr(rots_c), _ptr(cov_c),
+                    _ptr(view), _ptr(proj), _ptr(campos), float(rs.tanfovx), float(rs.tanfovy),
+                    int(bool(rs.prefiltered)), radii.data_ptr(), geom.data_ptr(), img.data_ptr(),
+                    counts.data_ptr(), sp, int(debug)))
+                planned = torch.cuda.Event()
+                planned.record(stream)
+                cap = _capacity.guess(dev.index or 0, P)
+                while True:
+                    binning = torch.empty((_LIB.g4s_binning_bytes(cap),), dtype=torch.uint8, device=dev)
+                    if debug:
+                        planned.synchronize()
+                        if int(counts[0]) > cap:
+                            cap = int(counts[0])
+                            continue
+                    _lib.check(_LIB.g4s_forward_render(
+                        P, W, H, bg.data_ptr(), geom.data_ptr(), img.data_ptr(), binning.data_ptr(), cap,
+                        color.data_ptr(), others.data_ptr(), sp, int(debug)))
+                    if mode == "none":
+                        _pending_overflow.append((planned, counts, cap))
+                        num_rendered = -1
+                        break
+                    planned.synchronize()  # waits for project + scan only; the blend keeps running
+                    num_rendered = int(counts[0])
+                    _capacity.observe(dev.index or 0, num_rendered)
+                    if num_rendered <= cap:
+                        break
+                    cap = num_rendered + 65536  # the speculative launch was a no-op: re-issue
+                if debug and rs.prefiltered and int(counts[3]) != 0:
+                    raise RuntimeError("Point is filtered although prefiltered is set. This shouldn't happen!")
+                ctx.counts = counts
+
+        ctx.raster_settings = rs
+        ctx.num_rendered = num_rendered
+        ctx.M = M
+        ctx.save_for_backward(colors_c, means3D_c, scales_c, rots_c, cov_c, radii, sh_c, geom, binning, img)
+        ctx.mark_non_differentiable(radii)
+        return color, radii, others
+
+    @staticmethod
+    def backward(ctx, grad_out_color, grad_radii, grad_depth):
+        rs = ctx.raster_settings
+        colors_c, means3D_c, scales_c, rots_c, cov_c, radii, sh_c, geom, binning, img = ctx.saved_tensors
+        dev = means3D_c.device
+        P = int(means3D_c.size(0))
+        M = ctx.M
+        H, W = int(rs.image_height), int(rs.image_width)
+        f32 = dict(dtype=torch.float32, device=dev)
+        alloc = torch.zeros if P == 0 else torch.empty  # every element is written by the kernels
+        dL_dmeans3D = alloc((P, 3), **f32)
+        dL_dmeans2D = alloc((P, 3), **f32)
+        dL_dcolors = alloc((P, NUM_CHANNELS), **f32)
+        dL_dopacity = alloc((P, 1), **f32)
+        dL_dtransMat = alloc((P, 9), **f32)
+        dL_dsh = alloc((P, M, 3), **f32)
+        dL_dscales = alloc((P, 2), **f32)
+        dL_drotations = alloc((P, 4), **f32)
+        if P != 0:
+            if M > 0 and sh_c.numel() == 0:
+                dL_dsh.zero_()
+            g_color = _f32c(grad_out_color, "dL_dout_color")
+            g_others = _f32c(grad_depth, "dL_dout_others")
+            bg = _f32c(rs.bg, "background")
+            view = _f32c(rs.viewmatrix, "viewmatrix")
+            proj = _f32c(rs.projmatrix, "projmatrix")
+            campos = _f32c(rs.campos, "campos")
+            with torch.cuda.device(dev):
+                sp = torch.cuda.current_stream(dev).cuda_stream
+                scratch = torch.empty((_LIB.g4s_backward_scratch_bytes(P),), dtype=torch.uint8, device=dev)
+                _lib.check(_LIB.g4s_backward(
+                    P, int(rs.sh_degree), M, W, H, bg.data_ptr(), _ptr(means3D_c), _ptr(sh_c), _ptr(colors_c),
+                    _ptr(scales_c), float(rs.scale_modifier), _ptr(rots_c), _ptr(cov_c), _ptr(view), _ptr(proj),
+                    _ptr(campos), float(rs.tanfovx), float(rs.tanfovy), radii.data_ptr(), geom.data_ptr(),
+                    binning.data_ptr(), img.data_ptr(), g_color.data_ptr(), g_others.data_ptr(),
+                    dL_dmeans3D.data_ptr(), dL_dmeans2D.data_ptr(), _ptr(dL_dsh), dL_dcolors.data_ptr(),
+                    dL_dopacity.data_ptr(), dL_dscales.data_ptr(), dL_drotations.data_ptr(),
+                    dL_dtransMat.data_ptr(), scratch.data_ptr(), sp, int(bool(rs.debug))))
+        # same order as the reference (RAST/diff_surfel_rasterization/__init__.py:144-154)
+        return (dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales, dL_drotations,
+                dL_dtransMat, None)
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        """Boolean mask of points with view-space z > 0.2 (reference :177-186)."""
+        with torch.no_grad():
+            rs = self.raster_settings
+            pos = _f32c(positions, "means3D")
+            P = int(pos.size(0))
+            present = torch.zeros((P,), dtype=torch.bool, device=pos.device)
+            if P != 0:
+                view = _f32c(rs.viewmatrix, "viewmatrix")
+                proj = _f32c(rs.projmatrix, "projmatrix")
+                with torch.cuda.device(pos.device):
+                    sp = torch.cuda.current_stream(pos.device).cuda_stream
+                    _lib.check(_LIB.g4s_mark_visible(P, pos.data_ptr(), view.data_ptr(), proj.data_ptr(),
+                                                     present.data_ptr(), sp))
+        return present
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None,
+                rotations=None, cov3D_precomp=None):
+        raster_settings = self.raster_settings
+
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+
+        empty = torch.empty((0,), dtype=torch.float32, device=means3D.device)
+        if shs is None:
+            shs = empty
+        if colors_precomp is None:
+            colors_precomp = empty
+        if scales is None:
+            scales = empty
+        if rotations is None:
+            rotations = empty
+        if cov3D_precomp is None:
+            cov3D_precomp = empty
+
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                   cov3D_precomp, raster_settings)

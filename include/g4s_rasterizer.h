@@ -1,0 +1,139 @@
+/*
+ * g4s_rasterizer.h -- C ABI of the B200-native 2D-Gaussian (surfel) rasterizer.
+ *
+ * This is the drop-in boundary for the hot path of DaLi-Jack/G4Splat: it replaces the three
+ * entry points the reference binds with pybind11/libtorch
+ *   RAST = 2d-gaussian-splatting/submodules/diff-surfel-rasterization
+ *   RAST/ext.cpp:15-19                      PYBIND11_MODULE(_C): rasterize_gaussians,
+ *                                           rasterize_gaussians_backward, mark_visible
+ *   RAST/rasterize_points.h:17-67           their C++ signatures (torch::Tensor in / out)
+ *   RAST/cuda_rasterizer/rasterizer.h:24-86 CudaRasterizer::Rasterizer::{forward,backward,markVisible}
+ * with plain-pointer functions: no torch types, no C++ types, every buffer owned by the caller.
+ * All pointers are DEVICE pointers unless a parameter says "host".  Every launch goes to the
+ * `stream` argument (a cudaStream_t passed as void*; NULL = legacy default stream).  No call
+ * synchronises the host unless `debug` is non-zero (reference: CHECK_CUDA, auxiliary.h:295-302).
+ *
+ * Optional inputs follow the reference convention (RAST/diff_surfel_rasterization/__init__.py:
+ * 198-208 -> empty tensor -> null data pointer -> kernel branch): pass NULL.
+ *   exactly one of  shs | colors_precomp          must be non-NULL
+ *   exactly one of  (scales and rotations) | transMat_precomp   must be non-NULL
+ *
+ * Return value: 0 on success, a negative G4S_E* code otherwise; g4s_last_error() returns a
+ * thread-local human-readable string for the last failing call.
+ *
+ * Scratch buffers (the reference's geomBuffer / binningBuffer / imgBuffer byte tensors,
+ * RAST/rasterize_points.cu:89-96) are opaque byte blobs sized by the g4s_*_bytes() functions and
+ * must be kept alive, unmodified, from g4s_forward_* to the matching g4s_backward.
+ *
+ * Forward is split in two calls so that the host never has to block in the middle of the
+ * pipeline to size the per-tile instance lists (the reference does a blocking cudaMemcpy of
+ * num_rendered, rasterizer_impl.cu:282):
+ *   g4s_forward_plan    project + exact tile culling + per-tile counts + scan; copies
+ *                       {num_rendered, max tile list length} to `host_counts` asynchronously.
+ *   g4s_forward_render  scatter + per-tile depth sort + blend, for a binning buffer of
+ *                       `capacity` instances.  Every kernel in it checks num_rendered <= capacity
+ *                       on the device and turns into a no-op otherwise, so the caller may launch
+ *                       it speculatively with a guessed capacity, wait only for the plan event,
+ *                       and re-issue it with a larger buffer in the rare overflow case.
+ */
+#ifndef G4S_RASTERIZER_H_
+#define G4S_RASTERIZER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G4S_VERSION 100 /* 0.1.0 */
+
+enum {
+    G4S_OK = 0,
+    G4S_EINVAL = -1,   /* bad argument combination / sizes */
+    G4S_ECUDA = -2,    /* a CUDA runtime call or (debug) a kernel failed */
+    G4S_ECAPACITY = -3 /* debug only: num_rendered > capacity */
+};
+
+int g4s_version(void);
+const char* g4s_last_error(void);
+
+/* ---- scratch sizes ------------------------------------------------------------------------- */
+/* per-Gaussian state (projected records, clamp masks, depths): reference GeometryState,
+ * rasterizer_impl.cu:155-170 */
+size_t g4s_geom_bytes(int P);
+/* per-pixel + per-tile state (final T / M1 / M2, last + median contributor, tile counts,
+ * offsets): reference ImageState, rasterizer_impl.cu:172-179 */
+size_t g4s_image_bytes(int W, int H);
+/* per-instance state for `capacity` (Gaussian, tile) instances (unsorted 64-bit keys + sorted
+ * lists): reference BinningState, rasterizer_impl.cu:181-194 */
+size_t g4s_binning_bytes(int64_t capacity);
+/* backward scratch: per-Gaussian gradient accumulators of the blend stage (the reference's
+ * dL_dtransMat / dL_dnormal / dL_dcolors / dL_dmean2D temporaries, rasterize_points.cu:187-195) */
+size_t g4s_backward_scratch_bytes(int P);
+
+/* ---- forward ------------------------------------------------------------------------------- */
+/* Replaces the first half of CudaRasterizer::Rasterizer::forward (rasterizer_impl.cu:198-283).
+ * host_counts: PINNED host int32[4], filled asynchronously on `stream`:
+ *   [0] num_rendered (instances after exact tile culling)   [1] longest tile list
+ *   [2] number of visible Gaussians (radii > 0)              [3] reserved
+ * radii[P] (int32, output) is fully written here. */
+int g4s_forward_plan(int P, int D, int M, int W, int H,
+                     const float* means3D, const float* shs, const float* colors_precomp,
+                     const float* opacities, const float* scales, float scale_modifier,
+                     const float* rotations, const float* transMat_precomp,
+                     const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                     float tan_fovx, float tan_fovy, int prefiltered,
+                     int* radii, void* geom_buffer, void* img_buffer,
+                     int32_t* host_counts, void* stream, int debug);
+
+/* Replaces the second half of Rasterizer::forward (rasterizer_impl.cu:285-341).
+ * out_color[3,H,W], out_others[7,H,W] are fully written (callers need not zero them). */
+int g4s_forward_render(int P, int W, int H, const float* background,
+                       const void* geom_buffer, void* img_buffer,
+                       void* binning_buffer, int64_t capacity,
+                       float* out_color, float* out_others, void* stream, int debug);
+
+/* ---- backward ------------------------------------------------------------------------------ */
+/* Replaces CudaRasterizer::Rasterizer::backward (rasterizer_impl.cu:346-448) and the gradient
+ * allocation of RasterizeGaussiansBackwardCUDA (rasterize_points.cu:187-195): every output
+ * element is written (zeros for Gaussians that were not visible), callers need not zero them.
+ * Outputs (device): dL_dmeans3D[P,3] dL_dmeans2D[P,3] dL_dsh[P,M,3] (may be NULL when M == 0)
+ *   dL_dcolors[P,3] dL_dopacity[P] dL_dscales[P,2] dL_drotations[P,4] dL_dtransMat[P,9].
+ * scratch: g4s_backward_scratch_bytes(P) bytes. */
+int g4s_backward(int P, int D, int M, int W, int H, const float* background,
+                 const float* means3D, const float* shs, const float* colors_precomp,
+                 const float* scales, float scale_modifier, const float* rotations,
+                 const float* transMat_precomp, const float* viewmatrix, const float* projmatrix,
+                 const float* cam_pos, float tan_fovx, float tan_fovy, const int* radii,
+                 const void* geom_buffer, const void* binning_buffer, const void* img_buffer,
+                 const float* dL_dout_color, const float* dL_dout_others,
+                 float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors,
+                 float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dtransMat,
+                 void* scratch, void* stream, int debug);
+
+/* ---- markVisible --------------------------------------------------------------------------- */
+/* Replaces Rasterizer::markVisible / checkFrustum (rasterizer_impl.cu:54-66,141-153):
+ * present[i] = (viewmatrix * means3D[i]).z > 0.2.  present is uint8[P] (bool). */
+int g4s_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream);
+
+/* ---- introspection (tests, benchmarks) ----------------------------------------------------- */
+/* Copies decoded views of the opaque buffers into caller-provided DEVICE arrays (any may be
+ * NULL).  Lets stage-level parity tests compare against the oracle without knowing the layout.
+ *   transMat[P,9] means2D[P,2] normal_opacity[P,4] rgb[P,3] depths[P] bbox[P,4] clamped[P,3](u8)
+ *   tiles_touched[P](u32) */
+int g4s_debug_decode_geom(int P, const void* geom_buffer, float* transMat, float* means2D,
+                          float* normal_opacity, float* rgb, float* depths, float* bbox,
+                          uint8_t* clamped, uint32_t* tiles_touched, void* stream);
+/*   ranges[T,2](u32) final_T[3,H,W] n_contrib[2,H,W](u32); point_list[capacity](u32) */
+int g4s_debug_decode_lists(int W, int H, const void* img_buffer, const void* binning_buffer,
+                           int64_t capacity, uint32_t* ranges, float* final_T, uint32_t* n_contrib,
+                           uint32_t* point_list, void* stream);
+/* number of kernel launches issued by this library since process start (bench: gpu_launches) */
+int64_t g4s_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G4S_RASTERIZER_H_ */

@@ -1,0 +1,154 @@
+"""Shared test plumbing: one `Case` description, three ways to run it (CPU oracle, any operator
+module exposing the reference API on a CUDA device -- the B200 operator or the reference
+extension from oracle/_ref), and the parity metric of SURVEY.md 8d."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, Optional
+
+import numpy as np
+
+from g4splat_b200 import synthetic as S
+
+FWD_KEYS = ("color", "allmap", "radii")
+GRAD_KEYS = ("dL_dmeans3D", "dL_dmeans2D", "dL_dsh", "dL_dcolors", "dL_dopacity", "dL_dscales",
+             "dL_drotations", "dL_dtransMat")
+
+
+@dataclass
+class Case:
+    name: str
+    scene: Dict[str, np.ndarray]
+    cam: S.SyntheticCamera
+    sh_degree: int = 3
+    bg: np.ndarray = field(default_factory=lambda: np.zeros(3, np.float32))
+    scale_modifier: float = 1.0
+    colors_precomp: Optional[np.ndarray] = None    # [P,3]: replaces shs
+    transMat_precomp: Optional[np.ndarray] = None  # [P,9]: replaces scales / rotations
+    grad_seed: int = 0
+
+    @property
+    def P(self):
+        return int(self.scene["means3D"].shape[0])
+
+    def upstream(self):
+        return S.make_upstream_grads(self.cam.W, self.cam.H, self.grad_seed)
+
+
+def room_case(name="c0", P=10_000, W=256, H=256, seed=0, cam_index=0, cams=1, **kw) -> Case:
+    scene = S.make_scene(P, seed)
+    cam = S.make_cameras(cams, W, H)[cam_index]
+    return Case(name=name, scene=scene, cam=cam, grad_seed=seed, **kw)
+
+
+# --------------------------------------------------------------------------------- CPU oracle
+def run_oracle(oracle, case: Case, backward: bool = True):
+    sc, cam = case.scene, case.cam
+    use_sh = case.colors_precomp is None
+    use_sr = case.transMat_precomp is None
+    st = oracle.forward(
+        means3D=sc["means3D"], opacities=sc["opacities"], view=cam.viewmatrix, proj=cam.projmatrix,
+        campos=cam.campos, W=cam.W, H=cam.H, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=case.bg,
+        shs=sc["shs"] if use_sh else None, colors_precomp=None if use_sh else case.colors_precomp,
+        scales=sc["scales"] if use_sr else None, rotations=sc["rotations"] if use_sr else None,
+        transMat_precomp=None if use_sr else case.transMat_precomp,
+        sh_degree=case.sh_degree, scale_modifier=case.scale_modifier)
+    out = dict(color=st["out_color"], allmap=st["out_others"], radii=st["radii"], _state=st)
+    if backward:
+        gc, go = case.upstream()
+        g = oracle.backward(st, gc, go)
+        out.update(dL_dmeans3D=g["dL_dmeans3D"], dL_dmeans2D=g["dL_dmeans2D"], dL_dsh=g["dL_dsh"],
+                   dL_dcolors=g["dL_dcolors"], dL_dopacity=g["dL_dopacity"], dL_dscales=g["dL_dscales"],
+                   dL_drotations=g["dL_drotations"], dL_dtransMat=g["dL_dtransMat"])
+    return out
+
+
+# ------------------------------------------------------------------------ operator on the GPU
+def make_settings(mod, case: Case, device, debug=False):
+    import torch
+    cam = case.cam
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device)
+    return mod.GaussianRasterizationSettings(
+        image_height=cam.H, image_width=cam.W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=t(case.bg),
+        scale_modifier=case.scale_modifier, viewmatrix=t(cam.viewmatrix), projmatrix=t(cam.projmatrix),
+        sh_degree=case.sh_degree, campos=t(cam.campos), prefiltered=False, debug=debug)
+
+
+def run_operator(mod, case: Case, device="cuda", backward: bool = True, debug=False):
+    """Runs `mod.GaussianRasterizer` (reference API) and returns numpy outputs / grads."""
+    import torch
+    sc = case.scene
+    t = lambda a, rg=False: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device).requires_grad_(rg)
+    use_sh = case.colors_precomp is None
+    use_sr = case.transMat_precomp is None
+    means3D = t(sc["means3D"], backward)
+    means2D = torch.zeros_like(means3D, requires_grad=backward)
+    opac = t(sc["opacities"], backward)
+    shs = t(sc["shs"], backward) if use_sh else None
+    colors = None if use_sh else t(case.colors_precomp, backward)
+    scales = t(sc["scales"], backward) if use_sr else None
+    rots = t(sc["rotations"], backward) if use_sr else None
+    cov = None if use_sr else t(case.transMat_precomp, backward)
+    rast = mod.GaussianRasterizer(raster_settings=make_settings(mod, case, device, debug))
+    color, radii, allmap = rast(means3D=means3D, means2D=means2D, opacities=opac, shs=shs, colors_precomp=colors,
+                                scales=scales, rotations=rots, cov3D_precomp=cov)
+    out = dict(color=color.detach().cpu().numpy(), allmap=allmap.detach().cpu().numpy(),
+               radii=radii.detach().cpu().numpy())
+    if backward:
+        gc, go = case.upstream()
+        loss = (color * torch.from_numpy(gc).to(device)).sum() + (allmap * torch.from_numpy(go).to(device)).sum()
+        loss.backward()
+        z = lambda x, shape: (x.grad.detach().cpu().numpy() if x is not None and x.grad is not None
+                              else np.zeros(shape, np.float32))
+        P = case.P
+        M = sc["shs"].shape[1] if use_sh else 0
+        out.update(dL_dmeans3D=z(means3D, (P, 3)), dL_dmeans2D=z(means2D, (P, 3)), dL_dsh=z(shs, (P, M, 3)),
+                   dL_dcolors=z(colors, (P, 3)), dL_dopacity=z(opac, (P, 1)), dL_dscales=z(scales, (P, 2)),
+                   dL_drotations=z(rots, (P, 4)), dL_dtransMat=z(cov, (P, 9)))
+    torch.cuda.synchronize()
+    return out
+
+
+# -------------------------------------------------------------------------------- the metric
+def parity(x: np.ndarray, ref: np.ndarray, rtol: float = 1e-4):
+    """max_rel = |x - ref|_inf / |ref|_inf, and the fraction of elements outside
+    |x - ref| <= rtol * |ref|_inf + rtol * |ref|."""
+    x = np.asarray(x, dtype=np.float64).ravel()
+    ref = np.asarray(ref, dtype=np.float64).ravel()
+    assert x.shape == ref.shape, (x.shape, ref.shape)
+    if x.size == 0:
+        return dict(max_rel=0.0, bad_frac=0.0, scale=0.0, n=0)
+    scale = max(np.abs(ref).max(), 1e-30)
+    diff = np.abs(x - ref)
+    bad = diff > (rtol * scale + rtol * np.abs(ref))
+    bad |= ~np.isfinite(x) & np.isfinite(ref)
+    return dict(max_rel=float(np.nanmax(diff) / scale), bad_frac=float(bad.mean()), scale=float(scale), n=int(x.size))
+
+
+def report(a: dict, b: dict, keys, rtol=1e-4):
+    rows = {}
+    for k in keys:
+        if k == "radii":
+            rows[k] = dict(mismatch=int((np.asarray(a[k]) != np.asarray(b[k])).sum()), n=int(np.asarray(a[k]).size))
+        elif k == "allmap":
+            for c, nm in enumerate(("depth", "alpha", "nx", "ny", "nz", "median_depth", "distortion")):
+                rows[f"allmap[{c}:{nm}]"] = parity(a[k][c], b[k][c], rtol)
+        else:
+            rows[k] = parity(a[k], b[k], rtol)
+    return rows
+
+
+def assert_parity(a: dict, b: dict, keys, rtol=1e-4, max_bad_frac=0.0, max_rel=None, radii_mismatch=0, what=""):
+    rows = report(a, b, keys, rtol)
+    failures = []
+    for k, r in rows.items():
+        if "mismatch" in r:
+            if r["mismatch"] > radii_mismatch:
+                failures.append(f"{k}: {r['mismatch']} / {r['n']} radii differ")
+            continue
+        if r["bad_frac"] > max_bad_frac:
+            failures.append(f"{k}: {r['bad_frac']:.3e} of elements outside rtol={rtol} (max_rel {r['max_rel']:.3e})")
+        if max_rel is not None and r["max_rel"] > max_rel:
+            failures.append(f"{k}: max_rel {r['max_rel']:.3e} > {max_rel}")
+    assert not failures, what + "\n" + "\n".join(failures) + "\n" + "\n".join(f"{k}: {v}" for k, v in rows.items())
+    return rows
