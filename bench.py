@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- forward+backward Gaussians/s of the surfel rasterizer hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (all N): BASELINE.json config 2 -- synthetic "room" scan, 1.0 M surfels, SH degree 3,
+1920x1080, --views views per GPU per step cycled from a ring of 64 perimeter cameras; every
+rank holds the full scene, renders its own views forward+backward through the operator API
+(gradients accumulate in the parameter leaves) and, for N > 1, joins ONE NCCL all-reduce of the
+[P,60] gradient + densification-statistics buffer per step (weak scaling: per-GPU work fixed).
+
+  value   = P * views * N * K / t   with parameters, cameras and upstream gradients resident in
+            HBM; t = CUDA-event time of the K steps, max over ranks.
+  e2e     = same through the public API starting from HOST buffers: per view one pinned uint8
+            ground-truth image is copied host->device, an L1 photometric + regulariser loss is
+            formed on the device, and the scalar loss is read back device->host.
+  roofline= dominant kernel of the step (per-stage CUDA-event timers inside the C library,
+            averaged over the timed region) against the measured HBM peak; algorithmic bytes per
+            stage are spelled out in DESIGN.md and in `algorithmic_bytes()` below.
+  cpu_baseline = the CPU oracle port (oracle/surfel_oracle.c, OpenMP on all host cores) on ONE
+            full view of the same workload.
+
+--impl reference runs the UNMODIFIED reference extension (oracle/_ref, the vendored
+diff-surfel-rasterization compiled for sm_100a) through its own Python API in the same loops;
+when that build is absent it falls back to timing the CPU oracle port.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "gaussians_per_s_fwd_bwd_1080p"
+UNIT = "Gaussians/s"
+CONFIG = "c2"
+CAM_RING = 64
+
+
+# ------------------------------------------------------------------------------------------ util
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(stage: str, P: int, V: int, R: int, N: int, T: int, K: int, M: int) -> float:
+    """Compulsory bytes per launch of each stage (DESIGN.md 'Kernels'): every input read once,
+    every output written once, every (Gaussian, tile) instance written once and read once."""
+    rec = 96 + 4 + 4 + 8 + 1                       # record + depth + ntiles + rect + clamp mask
+    return {
+        "project_fwd": P * (40 + 4) + V * (12 * K + rec) + R * 4,
+        "tile_scan": T * 16,
+        "scatter": V * 16 + R * (8 + 4),
+        "tile_sort": R * (8 + 4) + T * 8,
+        "blend_fwd": R * (4 + 96) + N * 60 + T * 12,
+        "acc_clear": P * 80,
+        "blend_bwd": R * (4 + 96 + 80) + N * 60 + T * 12,
+        "project_bwd": P * (4 + 12 + 12 + 4 + 8 + 16 + 36 + 12 + 12 * M) + V * (80 + 96 + 40 + 12 * K),
+    }[stage]
+
+
+def path_bytes(P, V, R, N, K, M):
+    """Whole-path figure of SURVEY.md 8d: P(96+12M) + V(40+24K) + 80N + 20R."""
+    return P * (96 + 12 * M) + V * (40 + 24 * K) + 80 * N + 20 * R
+
+
+# ------------------------------------------------------------------------------------- workload
+class Workload:
+    def __init__(self, device, views_per_step: int, rank: int, world: int, cfg_name: str = CONFIG):
+        import torch
+        from g4splat_b200 import synthetic as S
+        cfg = S.CONFIGS[cfg_name]
+        self.cfg, self.device, self.vps, self.rank, self.world = cfg, device, views_per_step, rank, world
+        self.P, self.W, self.H = cfg["P"], cfg["W"], cfg["H"]
+        sc = S.make_scene(self.P, cfg["seed"])
+        t = lambda a: torch.from_numpy(a).to(device).requires_grad_(True)
+        # 58 floats per Gaussian (xyz 3, SH 48, opacity 1, scaling 2, rotation 4), already activated:
+        # the operator's inputs.  (The trainer's activations / cat of features_dc and features_rest sit
+        # outside the operator boundary -- SURVEY.md 8f "next" rows.)
+        self.params = {"xyz": t(sc["means3D"]), "features": t(sc["shs"]), "opacity": t(sc["opacities"]),
+                       "scaling": t(sc["scales"]), "rotation": t(sc["rotations"])}
+        self.cams = S.make_cameras(CAM_RING, self.W, self.H)
+        d = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device)
+        self.cam_dev = [dict(view=d(c.viewmatrix), proj=d(c.projmatrix), campos=d(c.campos)) for c in self.cams]
+        self.bg = torch.zeros(3, device=device)
+        gc, go = S.make_upstream_grads(self.W, self.H, cfg["seed"])
+        self.g_color, self.g_allmap = d(gc), d(go)
+        # e2e: 8 distinct pinned uint8 "photographs" (random content; the loss only needs the bytes to move)
+        rng = np.random.default_rng(123 + rank)
+        self.gt_host = [torch.from_numpy(rng.integers(0, 256, size=(3, self.H, self.W), dtype=np.uint8)).pin_memory()
+                        for _ in range(8)]
+        self.gt_dev = torch.empty((3, self.H, self.W), dtype=torch.uint8, device=device)
+
+    def view_ids(self, step: int):
+        base = (step * self.world + self.rank) * self.vps
+        return [(base + i) % CAM_RING for i in range(self.vps)]
+
+    def settings(self, mod, vid: int):
+        c, cd = self.cams[vid], self.cam_dev[vid]
+        return mod.GaussianRasterizationSettings(
+            image_height=self.H, image_width=self.W, tanfovx=c.tanfovx, tanfovy=c.tanfovy, bg=self.bg,
+            scale_modifier=1.0, viewmatrix=cd["view"], projmatrix=cd["proj"], sh_degree=3, campos=cd["campos"],
+            prefiltered=False, debug=False)
+
+    def rasterize(self, mod, vid: int):
+        import torch
+        p = self.params
+        means2D = torch.zeros_like(p["xyz"], requires_grad=True)
+        shs = p["features"]
+        rast = mod.GaussianRasterizer(raster_settings=self.settings(mod, vid))
+        color, radii, allmap = rast(means3D=p["xyz"], means2D=means2D, opacities=p["opacity"], shs=shs,
+                                    scales=p["scaling"], rotations=p["rotation"])
+        return color, radii, allmap, means2D
+
+
+def run_steps(wl: Workload, mod, sync, steps: int, first_step: int, e2e: bool):
+    """`steps` optimisation-step-shaped passes; returns the last loss value (e2e) or None."""
+    import torch
+    last = None
+    for s in range(first_step, first_step + steps):
+        loss_acc = None
+        for k, vid in enumerate(wl.view_ids(s)):
+            color, radii, allmap, means2D = wl.rasterize(mod, vid)
+            if e2e:
+                wl.gt_dev.copy_(wl.gt_host[(s + k) % len(wl.gt_host)], non_blocking=True)
+                gt = wl.gt_dev.to(torch.float32) * (1.0 / 255.0)
+                loss = (color - gt).abs().mean() + 0.05 * allmap[6].mean() + 0.01 * (allmap[0] + allmap[5]).mean() \
+                    + 0.01 * allmap[1:5].mean()
+                loss.backward()
+                loss_acc = loss.detach() if loss_acc is None else loss_acc + loss.detach()
+            else:
+                torch.autograd.backward([color, allmap], [wl.g_color, wl.g_allmap])
+            sync.add_view_stats(means2D.grad, radii)
+        sync.allreduce()
+        if e2e:
+            last = float(loss_acc.item())  # device -> host read of the step's result
+        sync.zero()
+    return last
+
+
+def time_region(fn, device, dist_on):
+    import torch
+    import torch.distributed as dist
+    if dist_on:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = fn()
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1)
+    if dist_on:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    return ms, out
+
+
+# ----------------------------------------------------------------------------------- CPU oracle
+def cpu_oracle_step(cfg_name: str = CONFIG, threads: int = 0):
+    """One full view (forward + backward) of the workload on the host cores with the oracle port."""
+    from g4splat_b200 import synthetic as S
+    from oracle.oracle import Oracle
+    cfg = S.CONFIGS[cfg_name]
+    o = Oracle("f32")
+    cores = o.set_threads(threads if threads > 0 else (os.cpu_count() or 1))
+    sc = S.make_scene(cfg["P"], cfg["seed"])
+    cam = S.make_cameras(CAM_RING, cfg["W"], cfg["H"])[0]
+    gc, go = S.make_upstream_grads(cfg["W"], cfg["H"], cfg["seed"])
+    t0 = time.perf_counter()
+    st = o.forward(means3D=sc["means3D"], opacities=sc["opacities"], view=cam.viewmatrix, proj=cam.projmatrix,
+                   campos=cam.campos, W=cam.W, H=cam.H, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=np.zeros(3, np.float32),
+                   shs=sc["shs"], scales=sc["scales"], rotations=sc["rotations"], sh_degree=3)
+    o.backward(st, gc, go)
+    dt = time.perf_counter() - t0
+    return cfg["P"] / dt, cores, dt
+
+
+# ----------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--views", type=int, default=8, help="views per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    warmup = max(args.warmup, 3)
+
+    ref_mod = None
+    if args.impl == "reference":
+        if rank != 0:
+            return 0  # rank 0 alone runs the reference arm
+        world = 1
+        sys.path.insert(0, str(ROOT / "oracle"))
+        try:
+            import build_ref
+            if build_ref.up_to_date():
+                ref_mod = build_ref.import_reference()
+        except Exception as ex:  # noqa: BLE001
+            sys.stderr.write(f"[bench] reference extension not loadable: {ex}\n")
+        import torch
+        if ref_mod is None or not torch.cuda.is_available():
+            # no GPU build of the reference: time the CPU port of its algorithm instead
+            value, cores, dt = cpu_oracle_step()
+            line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+                    "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                    "dtype": "f32", "data": "synthetic", "impl": "reference",
+                    "config": {"workload": "c2: 1.0M surfels, SH3, 1920x1080, 1 view (CPU port of the reference algorithm)"},
+                    "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                                     "sample": "1 view forward+backward, full c2 size"},
+                    "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                    "gpu_launches": 0}
+            print(json.dumps(line))
+            return 0
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback of the product path)")
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    dist_on = world > 1
+    if dist_on:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    from g4splat_b200 import _lib
+    from g4splat_b200.view_parallel import ViewShardedGradSync
+    if args.impl == "reference":
+        mod = ref_mod
+        lib = None
+    else:
+        import g4splat_b200.diff_surfel_rasterization as mod
+        lib = _lib.load()
+
+    wl = Workload(device, args.views, rank, world)
+    sync = ViewShardedGradSync(wl.params)
+    P, N = wl.P, wl.W * wl.H
+    T = ((wl.W + 15) // 16) * ((wl.H + 15) // 16)
+
+    # ---- device-resident throughput ("value") -------------------------------------------------
+    run_steps(wl, mod, sync, warmup, 0, e2e=False)
+    if lib is not None:
+        lib.g4s_profile_enable(1)
+    launches0 = lib.g4s_launch_count() if lib is not None else 0
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms, _ = time_region(lambda: run_steps(wl, mod, sync, args.steps, warmup, e2e=False), device, dist_on)
+    clk = clocks.stop() if rank == 0 else None
+    launches = (lib.g4s_launch_count() - launches0) if lib is not None else None
+    stage_ms, stage_n = {}, {}
+    if lib is not None:
+        import ctypes as C
+        n_st = lib.g4s_profile_num_stages()
+        buf, cnt = (C.c_float * n_st)(), (C.c_int64 * n_st)()
+        lib.g4s_profile_read(buf, cnt, n_st)
+        lib.g4s_profile_enable(0)
+        for i in range(n_st):
+            nm = lib.g4s_profile_stage_name(i).decode()
+            stage_ms[nm], stage_n[nm] = float(buf[i]), int(cnt[i])
+    value = P * args.views * world * args.steps / (ms * 1e-3)
+
+    # ---- end to end from host buffers ("e2e") ---------------------------------------------------
+    run_steps(wl, mod, sync, 2, 1000, e2e=True)
+    ms_e2e, _ = time_region(lambda: run_steps(wl, mod, sync, args.steps, 1002, e2e=True), device, dist_on)
+    e2e_value = P * args.views * world * args.steps / (ms_e2e * 1e-3)
+    h2d = args.views * (3 * N)          # one uint8 image per view
+    d2h = 4                             # the scalar loss
+
+    if rank != 0:
+        if dist_on:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = load_peaks()
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world if args.impl != "reference" else args.gpus,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"c2: 1.0M surfels, SH degree 3, 1920x1080, {args.views} views/GPU/step from a ring of "
+                                   f"{CAM_RING} cameras, fwd+bwd{' + 1 NCCL all-reduce of [P,60] grads' if world > 1 else ''}",
+                       "P": P, "width": wl.W, "height": wl.H, "views_per_gpu_per_step": args.views,
+                       "l2_policy": "inputs larger than L2: 232 MB of parameters + 192 MB of SH gradients per view, a different camera every view",
+                       "parallelism": f"view-sharded dp{world}"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clk}
+    if args.impl == "reference":
+        line["impl"] = "reference"
+        line["gpu_launches"] = None
+        line["cpu_baseline"] = {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
+                                "sample": "the unmodified reference CUDA extension (oracle/_ref, sm_100a) on the same B200; "
+                                          "the reference has no CPU implementation of this path"}
+    else:
+        import g4splat_b200.diff_surfel_rasterization as op
+        V, R = op.last_counts["visible"], op.last_counts["num_rendered"]
+        Kc, M = 16, 16
+        dom = max((k for k in stage_ms if stage_ms[k] > 0), key=lambda k: stage_ms[k], default=None)
+        if dom is not None:
+            ab = algorithmic_bytes(dom, P, V, R, N, T, Kc, M)
+            achieved = ab / (stage_ms[dom] * 1e-3) / 1e9
+            traffic = None
+            tp = ROOT / "profiles" / "traffic.json"
+            if tp.exists():
+                traffic = json.loads(tp.read_text()).get(dom)
+            line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                                "algorithmic_bytes_per_launch": ab, "kernel_ms": stage_ms[dom],
+                                "note": "blend kernels are FP32-issue bound, not HBM bound (DESIGN.md); see stages/path"}
+        per_view_ms = sum(v for v in stage_ms.values() if v > 0)
+        line["stages"] = {k: {"ms": stage_ms[k], "launches": stage_n[k],
+                              "alg_GBps": (algorithmic_bytes(k, P, V, R, N, T, Kc, M) / (stage_ms[k] * 1e-3) / 1e9) if stage_ms[k] > 0 else None}
+                          for k in stage_ms}
+        pb = path_bytes(P, V, R, N, Kc, M)
+        line["path"] = {"alg_bytes_per_view": pb, "kernel_ms_per_view": per_view_ms, "visible": V, "num_rendered": R,
+                        "hbm_frac_of_kernel_time": (pb / (per_view_ms * 1e-3) / 1e9 / peak) if per_view_ms > 0 else None,
+                        "hbm_frac_of_step_time": pb * args.views / (ms / args.steps * 1e-3) / 1e9 / peak}
+        if not args.no_cpu_baseline and world == 1:
+            v, cores, dt = cpu_oracle_step()
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"1 view forward+backward at full c2 size, {dt:.1f} s"}
+    print(json.dumps(line))
+    if dist_on:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

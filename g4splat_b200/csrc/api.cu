@@ -30,11 +30,64 @@ static int stage_check(bool debug, cudaStream_t s, const char* stage) {
     if (debug) return check_cuda(cudaStreamSynchronize(s), stage);
     return G4S_OK;
 }
+
+// ---- optional per-stage CUDA-event timers (bench / profiling only; process-global) -------------
+enum { ST_PROJECT_FWD = 0, ST_TILE_SCAN, ST_SCATTER, ST_TILE_SORT, ST_BLEND_FWD, ST_ACC_CLEAR, ST_BLEND_BWD,
+       ST_PROJECT_BWD, ST_COUNT };
+static const char* const kStageNames[ST_COUNT] = {"project_fwd", "tile_scan", "scatter", "tile_sort", "blend_fwd",
+                                                  "acc_clear", "blend_bwd", "project_bwd"};
+static bool g_profile = false;
+static cudaEvent_t g_ev_begin[ST_COUNT], g_ev_end[ST_COUNT];
+static bool g_ev_valid[ST_COUNT] = {false};
+static bool g_ev_created = false;
+static double g_ev_sum_ms[ST_COUNT] = {0};
+static long long g_ev_n[ST_COUNT] = {0};
+// fold the previous launch of `stage` into the running mean if its events have completed
+static void harvest(int stage, bool wait) {
+    if (!g_ev_valid[stage]) return;
+    if (wait) { if (cudaEventSynchronize(g_ev_end[stage]) != cudaSuccess) return; }
+    else if (cudaEventQuery(g_ev_end[stage]) != cudaSuccess) { cudaGetLastError(); g_ev_valid[stage] = false; return; }
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_ev_begin[stage], g_ev_end[stage]) == cudaSuccess) { g_ev_sum_ms[stage] += ms; g_ev_n[stage]++; }
+    g_ev_valid[stage] = false;
+}
+struct StageTimer {
+    int stage; cudaStream_t s;
+    StageTimer(int st, cudaStream_t stream) : stage(st), s(stream) {
+        if (g_profile) { harvest(stage, false); cudaEventRecord(g_ev_begin[stage], s); }
+    }
+    ~StageTimer() {
+        if (g_profile) { cudaEventRecord(g_ev_end[stage], s); g_ev_valid[stage] = true; }
+    }
+};
 }  // namespace g4s
 
 using namespace g4s;
 
 extern "C" {
+
+int g4s_profile_enable(int on) {
+    if (on && !g_ev_created) {
+        for (int i = 0; i < ST_COUNT; i++) {
+            if (cudaEventCreate(&g_ev_begin[i]) != cudaSuccess || cudaEventCreate(&g_ev_end[i]) != cudaSuccess)
+                return fail(G4S_ECUDA, "g4s_profile_enable: cudaEventCreate failed");
+        }
+        g_ev_created = true;
+    }
+    g_profile = on != 0;
+    for (int i = 0; i < ST_COUNT; i++) { g_ev_valid[i] = false; g_ev_sum_ms[i] = 0; g_ev_n[i] = 0; }
+    return G4S_OK;
+}
+int g4s_profile_num_stages(void) { return ST_COUNT; }
+const char* g4s_profile_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : ""; }
+int g4s_profile_read(float* mean_ms_out, int64_t* count_out, int n) {
+    for (int i = 0; i < n && i < ST_COUNT; i++) {
+        harvest(i, true);
+        mean_ms_out[i] = g_ev_n[i] ? (float)(g_ev_sum_ms[i] / (double)g_ev_n[i]) : -1.0f;
+        if (count_out) count_out[i] = g_ev_n[i];
+    }
+    return G4S_OK;
+}
 
 int g4s_version(void) { return G4S_VERSION; }
 const char* g4s_last_error(void) { return g_error.c_str(); }
@@ -84,13 +137,13 @@ int g4s_forward_plan(int P, int D, int M, int W, int H, const float* means3D, co
     pa.scales = scales; pa.scale_modifier = scale_modifier; pa.rotations = rotations; pa.transMat_precomp = transMat_precomp;
     pa.view = viewmatrix; pa.proj = projmatrix; pa.campos = cam_pos;
     pa.radii = radii; pa.geom = geom; pa.tile_count = img.tile_count; pa.counters = img.counters;
-    launch_project_fwd(pa, s);
+    { StageTimer tm(ST_PROJECT_FWD, s); launch_project_fwd(pa, s); }
     if ((rc = stage_check(debug, s, "project_fwd"))) return rc;
 
     TileScanArgs ta;
     ta.num_tiles = T; ta.tile_count = img.tile_count; ta.tile_offset = img.tile_offset;
     ta.tile_order = img.tile_order; ta.counters = img.counters;
-    launch_tile_scan(ta, s);
+    { StageTimer tm(ST_TILE_SCAN, s); launch_tile_scan(ta, s); }
     if ((rc = stage_check(debug, s, "tile_scan"))) return rc;
 
     if (host_counts) {
@@ -98,8 +151,11 @@ int g4s_forward_plan(int P, int D, int M, int W, int H, const float* means3D, co
                              "copy counters")))
             return rc;
     }
-    if (debug && host_counts && prefiltered && host_counts[3] != 0)
-        return fail(G4S_ECUDA, "Point is filtered although prefiltered is set. This shouldn't happen!");
+    if (debug && host_counts) {
+        if ((rc = check_cuda(cudaStreamSynchronize(s), "copy counters"))) return rc;
+        if (prefiltered && host_counts[3] != 0)
+            return fail(G4S_ECUDA, "Point is filtered although prefiltered is set. This shouldn't happen!");
+    }
     return G4S_OK;
 }
 
@@ -127,13 +183,13 @@ int g4s_forward_render(int P, int W, int H, const float* background, const void*
     ScatterArgs sa;
     sa.P = P; sa.grid_x = gx; sa.capacity = capacity; sa.geom = geom; sa.tile_offset = img.tile_offset;
     sa.tile_cursor = img.tile_count; sa.keys = bin.keys; sa.counters = img.counters;
-    launch_scatter(sa, s);
+    { StageTimer tm(ST_SCATTER, s); launch_scatter(sa, s); }
     if ((rc = stage_check(debug, s, "scatter"))) return rc;
 
     TileSortArgs ts;
     ts.num_tiles = gx * gy; ts.capacity = capacity; ts.tile_offset = img.tile_offset; ts.tile_order = img.tile_order;
     ts.keys = bin.keys; ts.list = bin.list; ts.counters = img.counters;
-    launch_tile_sort(ts, s);
+    { StageTimer tm(ST_TILE_SORT, s); launch_tile_sort(ts, s); }
     if ((rc = stage_check(debug, s, "tile_sort"))) return rc;
 
     BlendFwdArgs ba;
@@ -141,7 +197,7 @@ int g4s_forward_render(int P, int W, int H, const float* background, const void*
     ba.tile_offset = img.tile_offset; ba.tile_order = img.tile_order; ba.list = bin.list; ba.rec = geom.rec;
     ba.bg = background; ba.final_T = img.final_T; ba.n_contrib = img.n_contrib;
     ba.out_color = out_color; ba.out_others = out_others; ba.counters = img.counters;
-    launch_blend_fwd(ba, s);
+    { StageTimer tm(ST_BLEND_FWD, s); launch_blend_fwd(ba, s); }
     return stage_check(debug, s, "blend_fwd");
 }
 
@@ -172,7 +228,10 @@ int g4s_backward(int P, int D, int M, int W, int H, const float* background, con
     bin_layout(1, (char*)binning_buffer, &bin);  // the sorted list is at offset 0 for every capacity
     int rc;
     float4* acc = (float4*)scratch;
-    if ((rc = check_cuda(cudaMemsetAsync(acc, 0, (size_t)P * ACC_FLOATS * sizeof(float), s), "memset acc"))) return rc;
+    {
+        StageTimer tm(ST_ACC_CLEAR, s);
+        if ((rc = check_cuda(cudaMemsetAsync(acc, 0, (size_t)P * ACC_FLOATS * sizeof(float), s), "memset acc"))) return rc;
+    }
 
     BlendBwdArgs bb;
     bb.W = W; bb.H = H; bb.grid_x = gx; bb.grid_y = gy;
@@ -180,7 +239,7 @@ int g4s_backward(int P, int D, int M, int W, int H, const float* background, con
     bb.list = bin.list;
     bb.rec = geom.rec; bb.bg = background; bb.final_T = img.final_T; bb.n_contrib = img.n_contrib;
     bb.dL_dpix = dL_dout_color; bb.dL_dothers = dL_dout_others; bb.acc = acc;
-    launch_blend_bwd(bb, s);
+    { StageTimer tm(ST_BLEND_BWD, s); launch_blend_bwd(bb, s); }
     if ((rc = stage_check(debug, s, "blend_bwd"))) return rc;
 
     ProjectBwdArgs pb;
@@ -192,7 +251,7 @@ int g4s_backward(int P, int D, int M, int W, int H, const float* background, con
     pb.dL_dmeans3D = dL_dmeans3D; pb.dL_dmeans2D = dL_dmeans2D; pb.dL_dsh = (M > 0 && shs) ? dL_dsh : nullptr;
     pb.dL_dcolors = dL_dcolors; pb.dL_dopacity = dL_dopacity; pb.dL_dscales = dL_dscales; pb.dL_drots = dL_drotations;
     pb.dL_dtransMat = dL_dtransMat;
-    launch_project_bwd(pb, s);
+    { StageTimer tm(ST_PROJECT_BWD, s); launch_project_bwd(pb, s); }
     return stage_check(debug, s, "project_bwd");
 }
 

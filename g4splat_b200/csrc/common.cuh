@@ -172,8 +172,14 @@ __device__ __forceinline__ void build_T(f3 p, float sx, float sy, const f3 R[3],
     }
     const float hw = float(W) / 2.0f, hw1 = float(W - 1) / 2.0f;
     const float hh = float(H) / 2.0f, hh1 = float(H - 1) / 2.0f;
-    Tu = mk3(X[0][0] * hw + X[3][0] * hw1, X[0][1] * hw + X[3][1] * hw1, X[0][2] * hw + X[3][2] * hw1);
-    Tv = mk3(X[1][0] * hh + X[3][0] * hh1, X[1][1] * hh + X[3][1] * hh1, X[1][2] * hh + X[3][2] * hh1);
+    // The reference sums X0*hw + X1*0 + X2*0 + X3*hw1 left to right; nvcc contracts that to
+    // fma(X3, hw1, round(X0*hw)) (the zero terms are exact no-ops).  Spelled with intrinsics so
+    // that the rounding points are the reference's: the ray-splat solve is ill-conditioned
+    // (pix*Tw - Tu cancels ~3 digits), one ulp in T moves alpha by 1e-5 and flips thresholds.
+    Tu = mk3(__fmaf_rn(X[3][0], hw1, __fmul_rn(X[0][0], hw)), __fmaf_rn(X[3][1], hw1, __fmul_rn(X[0][1], hw)),
+             __fmaf_rn(X[3][2], hw1, __fmul_rn(X[0][2], hw)));
+    Tv = mk3(__fmaf_rn(X[3][0], hh1, __fmul_rn(X[1][0], hh)), __fmaf_rn(X[3][1], hh1, __fmul_rn(X[1][1], hh)),
+             __fmaf_rn(X[3][2], hh1, __fmul_rn(X[1][2], hh)));
     Tw = mk3(X[3][0], X[3][1], X[3][2]);
 }
 

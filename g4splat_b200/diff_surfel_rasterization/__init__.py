@@ -67,6 +67,9 @@ class _CapacityPolicy:
 
 
 _capacity = _CapacityPolicy()
+# (num_rendered, longest tile list, visible Gaussians) of the most recent forward whose plan the
+# host has waited for; benchmarks read it to size the algorithmic-bytes model
+last_counts = {"num_rendered": 0, "max_tile_list": 0, "visible": 0}
 _pending_overflow = []  # (event, pinned counts, capacity) of G4S_SYNC=none calls not yet checked
 _RING = 256             # pinned count slots; a slot is reused only after _RING further forwards
 _ring = None
@@ -181,6 +184,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                         break
                     planned.synchronize()  # waits for project + scan only; the blend keeps running
                     num_rendered = int(counts[0])
+                    last_counts.update(num_rendered=num_rendered, max_tile_list=int(counts[1]), visible=int(counts[2]))
                     _capacity.observe(dev.index or 0, num_rendered)
                     if num_rendered <= cap:
                         break

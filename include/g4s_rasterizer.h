@@ -132,6 +132,17 @@ int g4s_debug_decode_lists(int W, int H, const void* img_buffer, const void* bin
                            uint32_t* point_list, void* stream);
 /* number of kernel launches issued by this library since process start (bench: gpu_launches) */
 int64_t g4s_launch_count(void);
+/* Per-stage CUDA-event timers on the launch stream (process-global, for bench.py / profiling;
+ * the reference only times whole iterations, train_with_refine_depth.py:279-280,364,498).
+ * While enabled every stage launch is bracketed by two events; completed brackets are folded
+ * into a running mean without blocking.  g4s_profile_read waits for the last brackets and
+ * fills mean_ms_out[i] (-1 when stage i never ran) and count_out[i] (may be NULL) since the
+ * last g4s_profile_enable.  Stage order:
+ * project_fwd, tile_scan, scatter, tile_sort, blend_fwd, acc_clear, blend_bwd, project_bwd. */
+int g4s_profile_enable(int on);
+int g4s_profile_num_stages(void);
+const char* g4s_profile_stage_name(int i);
+int g4s_profile_read(float* mean_ms_out, int64_t* count_out, int n);
 
 #ifdef __cplusplus
 }

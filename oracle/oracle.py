@@ -138,6 +138,8 @@ class Oracle:
             dL_dsh=np.zeros((P, M, 3), rt), dL_dscales=np.zeros((P, 2), rt),
             dL_drotations=np.zeros((P, 4), rt))
         if P == 0:
+            g["blend_dL_dtransMat"] = g["dL_dtransMat"].copy()
+            g["blend_dL_dmean2D"] = g["dL_dmeans2D"].copy()
             return g
         self.lib.orc_blend_backward(
             C.c_int(W), C.c_int(H), _ptr(st["ranges"]), _ptr(st["point_list"]), _ptr(st["_bg"]),

@@ -41,6 +41,37 @@ def room_case(name="c0", P=10_000, W=256, H=256, seed=0, cam_index=0, cams=1, **
     return Case(name=name, scene=scene, cam=cam, grad_seed=seed, **kw)
 
 
+NAMED_CASES = {
+    # name: kwargs of room_case (+ "precomp": derive colors_precomp / transMat_precomp from the oracle)
+    "c0": dict(P=10_000, W=256, H=256, seed=0),
+    "c0_bg": dict(P=10_000, W=256, H=256, seed=5, bg=[0.3, 0.6, 0.9]),
+    "c0_deg0": dict(P=10_000, W=256, H=256, seed=6, sh_degree=0),
+    "c0_deg1": dict(P=6_000, W=200, H=120, seed=9, sh_degree=1, cams=4, cam_index=2),
+    "c0_precomp": dict(P=10_000, W=256, H=256, seed=8, precomp=True),
+    "ragged": dict(P=5_000, W=250, H=131, seed=7, sh_degree=2),
+    "scalemod": dict(P=4_000, W=160, H=96, seed=10, scale_modifier=0.7),
+    "tiny": dict(P=1_500, W=72, H=40, seed=21, bg=[1.0, 1.0, 1.0]),
+}
+
+
+def case_from_meta(meta: dict, oracle=None) -> Case:
+    kw = dict(meta)
+    name = kw.pop("name", "case")
+    precomp = kw.pop("precomp", False)
+    if "bg" in kw:
+        kw["bg"] = np.asarray(kw["bg"], np.float32)
+    case = room_case(name, **kw)
+    if precomp:
+        st = run_oracle(oracle, case, backward=False)["_state"]
+        case.colors_precomp = st["rgb"].copy()
+        case.transMat_precomp = st["transMats"].copy()
+    return case
+
+
+def named_case(name: str, oracle=None) -> Case:
+    return case_from_meta(dict(NAMED_CASES[name], name=name), oracle)
+
+
 # --------------------------------------------------------------------------------- CPU oracle
 def run_oracle(oracle, case: Case, backward: bool = True):
     sc, cam = case.scene, case.cam
@@ -57,9 +88,16 @@ def run_oracle(oracle, case: Case, backward: bool = True):
     if backward:
         gc, go = case.upstream()
         g = oracle.backward(st, gc, go)
+        # API view: gradients of arguments that were not passed are not observable (autograd drops
+        # them), so they compare as zeros; the stage-level accumulators stay available with a
+        # leading underscore.
+        zeros = np.zeros_like
         out.update(dL_dmeans3D=g["dL_dmeans3D"], dL_dmeans2D=g["dL_dmeans2D"], dL_dsh=g["dL_dsh"],
-                   dL_dcolors=g["dL_dcolors"], dL_dopacity=g["dL_dopacity"], dL_dscales=g["dL_dscales"],
-                   dL_drotations=g["dL_drotations"], dL_dtransMat=g["dL_dtransMat"])
+                   dL_dcolors=g["dL_dcolors"] if not use_sh else zeros(g["dL_dcolors"]),
+                   dL_dopacity=g["dL_dopacity"], dL_dscales=g["dL_dscales"], dL_drotations=g["dL_drotations"],
+                   dL_dtransMat=g["dL_dtransMat"] if not use_sr else zeros(g["dL_dtransMat"]),
+                   _blend_dL_dcolors=g["dL_dcolors"], _blend_dL_dtransMat=g["blend_dL_dtransMat"],
+                   _blend_dL_dmean2D=g["blend_dL_dmean2D"], _dL_dnormal=g["dL_dnormal"])
     return out
 
 
@@ -110,7 +148,14 @@ def run_operator(mod, case: Case, device="cuda", backward: bool = True, debug=Fa
 
 
 # -------------------------------------------------------------------------------- the metric
-def parity(x: np.ndarray, ref: np.ndarray, rtol: float = 1e-4):
+# The distortion channel is a sum of w * (m^2 A + M2 - 2 m M1) whose three O(1) terms cancel to
+# ~1e-6 on single-layer surfaces: its fp32 error is ~1e-7 ABSOLUTE whatever the result is (two
+# runs of differently-contracted but equally valid fp32 code differ by that much), so it is
+# compared against the natural scale of the terms (m in [0,1]) rather than against its own max.
+DISTORTION_SCALE_FLOOR = 1e-2
+
+
+def parity(x: np.ndarray, ref: np.ndarray, rtol: float = 1e-4, scale_floor: float = 1e-30):
     """max_rel = |x - ref|_inf / |ref|_inf, and the fraction of elements outside
     |x - ref| <= rtol * |ref|_inf + rtol * |ref|."""
     x = np.asarray(x, dtype=np.float64).ravel()
@@ -118,7 +163,7 @@ def parity(x: np.ndarray, ref: np.ndarray, rtol: float = 1e-4):
     assert x.shape == ref.shape, (x.shape, ref.shape)
     if x.size == 0:
         return dict(max_rel=0.0, bad_frac=0.0, scale=0.0, n=0)
-    scale = max(np.abs(ref).max(), 1e-30)
+    scale = max(np.abs(ref).max(), scale_floor)
     diff = np.abs(x - ref)
     bad = diff > (rtol * scale + rtol * np.abs(ref))
     bad |= ~np.isfinite(x) & np.isfinite(ref)
@@ -132,7 +177,8 @@ def report(a: dict, b: dict, keys, rtol=1e-4):
             rows[k] = dict(mismatch=int((np.asarray(a[k]) != np.asarray(b[k])).sum()), n=int(np.asarray(a[k]).size))
         elif k == "allmap":
             for c, nm in enumerate(("depth", "alpha", "nx", "ny", "nz", "median_depth", "distortion")):
-                rows[f"allmap[{c}:{nm}]"] = parity(a[k][c], b[k][c], rtol)
+                rows[f"allmap[{c}:{nm}]"] = parity(a[k][c], b[k][c], rtol,
+                                                   DISTORTION_SCALE_FLOOR if c == 6 else 1e-30)
         else:
             rows[k] = parity(a[k], b[k], rtol)
     return rows

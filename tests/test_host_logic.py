@@ -1,0 +1,118 @@
+"""Host-side logic of the operator shim and the view-sharding helpers (no GPU needed)."""
+import numpy as np
+import pytest
+import torch
+
+
+def test_one_of_exceptions_match_the_reference_text():
+    """RAST/diff_surfel_rasterization/__init__.py:192-196 -- raised before any device work."""
+    import g4splat_b200.diff_surfel_rasterization as op
+    rs = op.GaussianRasterizationSettings(16, 16, 1.0, 1.0, torch.zeros(3), 1.0, torch.eye(4), torch.eye(4), 0,
+                                          torch.zeros(3), False, False)
+    r = op.GaussianRasterizer(rs)
+    x = torch.zeros(4, 3)
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        r(x, x, torch.zeros(4, 1), shs=None, colors_precomp=None, scales=torch.zeros(4, 2), rotations=torch.zeros(4, 4))
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        r(x, x, torch.zeros(4, 1), shs=torch.zeros(4, 16, 3), colors_precomp=torch.zeros(4, 3),
+          scales=torch.zeros(4, 2), rotations=torch.zeros(4, 4))
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair or precomputed 3D covariance"):
+        r(x, x, torch.zeros(4, 1), shs=torch.zeros(4, 16, 3), scales=torch.zeros(4, 2))
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair or precomputed 3D covariance"):
+        r(x, x, torch.zeros(4, 1), shs=torch.zeros(4, 16, 3), scales=torch.zeros(4, 2), rotations=torch.zeros(4, 4),
+          cov3D_precomp=torch.zeros(4, 9))
+
+
+def test_settings_fields_match_the_reference():
+    import g4splat_b200.diff_surfel_rasterization as op
+    assert op.GaussianRasterizationSettings._fields == (
+        "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix", "projmatrix",
+        "sh_degree", "campos", "prefiltered", "debug")
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    """No CPU fallback: a CPU tensor must raise, not silently compute somewhere else."""
+    import g4splat_b200.diff_surfel_rasterization as op
+    rs = op.GaussianRasterizationSettings(16, 16, 1.0, 1.0, torch.zeros(3), 1.0, torch.eye(4), torch.eye(4), 0,
+                                          torch.zeros(3), False, False)
+    r = op.GaussianRasterizer(rs)
+    x = torch.zeros(4, 3)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        r(x, x, torch.zeros(4, 1), shs=torch.zeros(4, 16, 3), scales=torch.zeros(4, 2), rotations=torch.zeros(4, 4))
+
+
+def test_install_registers_the_reference_import_name():
+    import sys
+    import g4splat_b200
+    mod = g4splat_b200.install()
+    import diff_surfel_rasterization as d
+    assert d is mod and hasattr(d, "GaussianRasterizer") and hasattr(d, "rasterize_gaussians")
+    del sys.modules["diff_surfel_rasterization"]
+
+
+def test_capacity_policy():
+    from g4splat_b200.diff_surfel_rasterization import _CapacityPolicy
+    p = _CapacityPolicy()
+    assert p.guess(0, 1_000_000) == 6_000_000
+    assert p.guess(0, 10) == 1 << 20
+    p.observe(0, 3_000_000)
+    assert p.guess(0, 1_000_000) == 4_500_000 + 65536
+    assert p.guess(1, 10) == 1 << 20  # per device
+
+
+def bitonic_ascending(keys):
+    """Python mirror of bitonic_sort_ascending (g4splat_b200/csrc/binning.cu): same index math."""
+    keys = list(keys)
+    n = len(keys)
+    m = 1
+    while m < n:
+        m <<= 1
+    half = m >> 1
+    k = 2
+    while k <= m:
+        hk = k >> 1
+        for i in range(half):
+            blk, within = divmod(i, hk)
+            lo, hi = blk * k + within, blk * k + k - 1 - within
+            if hi < n and keys[lo] > keys[hi]:
+                keys[lo], keys[hi] = keys[hi], keys[lo]
+        j = k >> 2
+        while j > 0:
+            for i in range(half):
+                lo = 2 * j * (i // j) + (i % j)
+                hi = lo + j
+                if hi < n and keys[lo] > keys[hi]:
+                    keys[lo], keys[hi] = keys[hi], keys[lo]
+            j >>= 1
+        k <<= 1
+    return keys
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 31, 32, 33, 100, 257, 1000])
+def test_bitonic_network_sorts_any_length(n):
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 1 << 62, size=n).tolist()
+    assert bitonic_ascending(keys) == sorted(keys)
+
+
+def test_shard_views_partition():
+    from g4splat_b200.view_parallel import shard_views
+    assert [len(shard_views(50, 4, r)) for r in range(4)] == [13, 13, 12, 12]
+    for n, w in [(64, 8), (5, 2), (3, 4), (0, 2), (7, 7)]:
+        got = [i for r in range(w) for i in shard_views(n, w, r)]
+        assert got == list(range(n))
+
+
+def test_synthetic_scene_is_seeded_and_well_formed():
+    from g4splat_b200 import synthetic as S
+    a, b = S.make_scene(2000, 3), S.make_scene(2000, 3)
+    for k in a:
+        assert a[k].dtype == np.float32 and np.array_equal(a[k], b[k])
+    assert a["shs"].shape == (2000, 16, 3) and a["rotations"].shape == (2000, 4)
+    assert np.allclose(np.linalg.norm(a["rotations"], axis=1), 1, atol=1e-5)
+    assert (a["opacities"] > 0).all() and (a["opacities"] < 1).all()
+    cam = S.make_cameras(3, 320, 200)[1]
+    # view matrix is a rigid transform, camera centre maps to the origin
+    R = cam.viewmatrix.T[:3, :3]
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-5)
+    assert np.allclose(cam.viewmatrix.T @ np.append(cam.campos, 1.0), [0, 0, 0, 1], atol=1e-4)
