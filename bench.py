@@ -257,9 +257,8 @@ def main():
         if rank != 0:
             return 0  # rank 0 alone runs the reference arm
         world = 1
-        sys.path.insert(0, str(ROOT / "oracle"))
-        try:
-            import build_ref
+                try:
+            from oracle import build_ref
             if build_ref.up_to_date():
                 ref_mod = build_ref.import_reference()
         except Exception as ex:  # noqa: BLE001

@@ -17,7 +17,6 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
-sys.path.insert(0, str(ROOT / "oracle"))
 
 import helpers as Hh  # noqa: E402
 
@@ -25,7 +24,7 @@ CASES = ["tiny", "scalemod", "c0_deg1", "ragged", "c0_bg", "c0_precomp"]
 
 
 def main():
-    import build_ref
+    from oracle import build_ref
     import torch
     from oracle.oracle import Oracle
     ref = build_ref.import_reference()

@@ -170,11 +170,23 @@ def parity(x: np.ndarray, ref: np.ndarray, rtol: float = 1e-4, scale_floor: floa
     return dict(max_rel=float(np.nanmax(diff) / scale), bad_frac=float(bad.mean()), scale=float(scale), n=int(x.size))
 
 
+def radii_mismatch(a, b, loose: bool = False) -> int:
+    """Radii are integers and must match exactly (strict: B200 kernels vs the reference extension,
+    which agree bit for bit).  loose=True is for comparisons with the CPU oracle, whose plain-IEEE
+    arithmetic (no FMA contraction, exact 1/sqrt instead of rsqrt.approx) differs by an ulp from
+    the GPU: splats whose 3-sigma disc grazes the camera plane have radii of 1e4..1e6 px computed
+    from a cancelling difference, and ceil() of that moves by 1e-4 relative."""
+    a, b = np.asarray(a, np.int64), np.asarray(b, np.int64)
+    r = np.maximum(a, b)
+    tol = np.where(r >= 4096, np.maximum(1, np.floor(1e-4 * r)), 0) if loose else np.zeros_like(r)
+    return int(((np.abs(a - b) > tol) | ((a > 0) != (b > 0))).sum())
+
+
 def report(a: dict, b: dict, keys, rtol=1e-4):
     rows = {}
     for k in keys:
         if k == "radii":
-            rows[k] = dict(mismatch=int((np.asarray(a[k]) != np.asarray(b[k])).sum()), n=int(np.asarray(a[k]).size))
+            rows[k] = dict(mismatch=radii_mismatch(a[k], b[k]), n=int(np.asarray(a[k]).size))
         elif k == "allmap":
             for c, nm in enumerate(("depth", "alpha", "nx", "ny", "nz", "median_depth", "distortion")):
                 rows[f"allmap[{c}:{nm}]"] = parity(a[k][c], b[k][c], rtol,
@@ -184,12 +196,12 @@ def report(a: dict, b: dict, keys, rtol=1e-4):
     return rows
 
 
-def assert_parity(a: dict, b: dict, keys, rtol=1e-4, max_bad_frac=0.0, max_rel=None, radii_mismatch=0, what=""):
+def assert_parity(a: dict, b: dict, keys, rtol=1e-4, max_bad_frac=0.0, max_rel=None, radii_budget=0, what=""):
     rows = report(a, b, keys, rtol)
     failures = []
     for k, r in rows.items():
         if "mismatch" in r:
-            if r["mismatch"] > radii_mismatch:
+            if r["mismatch"] > radii_budget:
                 failures.append(f"{k}: {r['mismatch']} / {r['n']} radii differ")
             continue
         if r["bad_frac"] > max_bad_frac:

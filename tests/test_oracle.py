@@ -18,7 +18,7 @@ def test_fp32_and_fp64_builds_agree(oracle32, oracle64):
     # fp32 vs fp64 differ by rounding only; a handful of threshold flips are allowed
     Hh.assert_parity(a, b, ("color", "allmap"), rtol=2e-4, max_bad_frac=2e-3, what="fp32 vs fp64 forward")
     Hh.assert_parity(a, b, Hh.GRAD_KEYS, rtol=2e-3, max_bad_frac=2e-3, what="fp32 vs fp64 backward")
-    assert (a["radii"] != b["radii"]).sum() <= 3
+    assert Hh.radii_mismatch(a["radii"], b["radii"], loose=True) <= 2
 
 
 def test_precomputed_colour_path_renders_the_same_image(oracle32):
@@ -86,7 +86,7 @@ def test_oracle_matches_reference_golden(path, oracle32):
     ref = {k: z[k] for k in Hh.FWD_KEYS + Hh.GRAD_KEYS}
     Hh.assert_parity(out, ref, ("color", "allmap"), rtol=1e-4, max_bad_frac=2e-4, what=f"{path.stem} forward")
     Hh.assert_parity(out, ref, Hh.GRAD_KEYS, rtol=1e-3, max_bad_frac=2e-4, what=f"{path.stem} backward")
-    assert (out["radii"] != ref["radii"]).sum() <= max(2, int(2e-4 * out["radii"].size))
+    assert Hh.radii_mismatch(out["radii"], ref["radii"], loose=True) <= 1
 
 
 def test_golden_vectors_are_present():

@@ -34,8 +34,7 @@ def b200():
 
 @pytest.fixture(scope="module")
 def reference():
-    sys.path.insert(0, str(ROOT / "oracle"))
-    import build_ref
+    from oracle import build_ref
     if not build_ref.up_to_date():
         pytest.skip("oracle/_ref not built (no /root/reference here and no prebuilt files)")
     return build_ref.import_reference()
@@ -51,7 +50,7 @@ def test_b200_matches_oracle(name, b200, oracle32):
     got = Hh.run_operator(b200, case)
     Hh.assert_parity(got, want, ("color", "allmap"), rtol=1e-4, max_bad_frac=FWD_BUDGET, what=f"{name} forward vs oracle")
     Hh.assert_parity(got, want, Hh.GRAD_KEYS, rtol=1e-3, max_bad_frac=GRAD_BUDGET, what=f"{name} backward vs oracle")
-    assert (got["radii"] != want["radii"]).sum() <= max(2, int(2e-4 * case.P))
+    assert Hh.radii_mismatch(got["radii"], want["radii"], loose=True) <= 1
 
 
 @pytest.mark.parametrize("path", sorted((ROOT / "tests" / "golden").glob("*.npz")), ids=lambda p: p.stem)
@@ -62,7 +61,7 @@ def test_b200_matches_reference_golden(path, b200, oracle32):
     ref = {k: z[k] for k in Hh.FWD_KEYS + Hh.GRAD_KEYS}
     Hh.assert_parity(got, ref, ("color", "allmap"), rtol=1e-4, max_bad_frac=FWD_BUDGET, what=f"{path.stem} forward vs golden")
     Hh.assert_parity(got, ref, Hh.GRAD_KEYS, rtol=1e-4, max_bad_frac=GRAD_BUDGET, what=f"{path.stem} backward vs golden")
-    assert (got["radii"] != ref["radii"]).sum() <= 1
+    assert Hh.radii_mismatch(got["radii"], ref["radii"]) == 0
 
 
 @pytest.mark.parametrize("name", SMALL)
@@ -72,7 +71,7 @@ def test_b200_matches_reference_side_by_side(name, b200, reference, oracle32):
     got = Hh.run_operator(b200, case)
     Hh.assert_parity(got, want, ("color", "allmap"), rtol=1e-4, max_bad_frac=FWD_BUDGET, what=f"{name} forward vs reference")
     Hh.assert_parity(got, want, Hh.GRAD_KEYS, rtol=1e-4, max_bad_frac=GRAD_BUDGET, what=f"{name} backward vs reference")
-    assert (got["radii"] != want["radii"]).sum() <= 1
+    assert Hh.radii_mismatch(got["radii"], want["radii"]) == 0
 
 
 @pytest.mark.parametrize("cfg", ["c1", "c2"])
@@ -85,7 +84,7 @@ def test_baseline_configs_match_reference(cfg, b200, reference):
     got = Hh.run_operator(b200, case)
     Hh.assert_parity(got, want, ("color", "allmap"), rtol=1e-4, max_bad_frac=FWD_BUDGET, what=f"{cfg} forward vs reference")
     Hh.assert_parity(got, want, Hh.GRAD_KEYS, rtol=1e-4, max_bad_frac=GRAD_BUDGET, what=f"{cfg} backward vs reference")
-    assert (got["radii"] != want["radii"]).sum() <= max(2, int(2e-5 * case.P))
+    assert Hh.radii_mismatch(got["radii"], want["radii"]) == 0
 
 
 def test_stage_level_projection_matches_oracle(b200, oracle32):

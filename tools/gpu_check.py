@@ -28,8 +28,7 @@ def load_ref():
     if os.environ.get("G4S_NO_REF"):
         return None
     try:
-        sys.path.insert(0, str(ROOT / "oracle"))
-        import build_ref
+        from oracle import build_ref
         if not build_ref.up_to_date():
             return None
         return build_ref.import_reference()
