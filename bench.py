@@ -257,7 +257,7 @@ def main():
         if rank != 0:
             return 0  # rank 0 alone runs the reference arm
         world = 1
-                try:
+        try:
             from oracle import build_ref
             if build_ref.up_to_date():
                 ref_mod = build_ref.import_reference()

@@ -25,6 +25,7 @@ SIGNATURES = {
     "g4s_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _f, _f,
                           _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "g4s_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
+    "g4s_densify_stats": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4s_profile_enable": (_i, [_i]),
     "g4s_profile_num_stages": (_i, []),
     "g4s_profile_stage_name": (C.c_char_p, [_i]),

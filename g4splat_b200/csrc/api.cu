@@ -119,6 +119,7 @@ int g4s_forward_plan(int P, int D, int M, int W, int H, const float* means3D, co
         if (shs && !cam_pos) return fail(G4S_EINVAL, "g4s_forward_plan: campos required with SHs");
         if (shs && (M < (D + 1) * (D + 1))) return fail(G4S_EINVAL, "g4s_forward_plan: M < (D+1)^2");
         if (D < 0 || D > 3) return fail(G4S_EINVAL, "g4s_forward_plan: sh degree must be 0..3");
+        if (shs && M > 16) return fail(G4S_EINVAL, "g4s_forward_plan: at most 16 SH coefficients (degree 3) are supported");
     }
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     if (gx > 65535 || gy > 65535) return fail(G4S_EINVAL, "g4s_forward_plan: image too large");
@@ -219,6 +220,7 @@ int g4s_backward(int P, int D, int M, int W, int H, const float* background, con
         !dL_dtransMat || !radii || !means3D || !background)
         return fail(G4S_EINVAL, "g4s_backward: null buffer");
     if (M > 0 && shs && !dL_dsh) return fail(G4S_EINVAL, "g4s_backward: dL_dsh required");
+    if (M > 16) return fail(G4S_EINVAL, "g4s_backward: at most 16 SH coefficients (degree 3) are supported");
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     GeomView geom;
     ImageView img;
@@ -263,6 +265,15 @@ int g4s_mark_visible(int P, const float* means3D, const float* viewmatrix, const
     if (!means3D || !viewmatrix || !present) return fail(G4S_EINVAL, "g4s_mark_visible: null buffer");
     launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
     return stage_check(false, (cudaStream_t)stream, "mark_visible");
+}
+
+int g4s_densify_stats(int P, const float* dL_dmeans2D, const int* radii, float* accum, float* denom,
+                      int* max_radii, void* stream) {
+    if (P < 0) return fail(G4S_EINVAL, "g4s_densify_stats: bad P");
+    if (P == 0) return G4S_OK;
+    if (!dL_dmeans2D || !radii || !accum || !denom || !max_radii) return fail(G4S_EINVAL, "g4s_densify_stats: null buffer");
+    launch_densify_stats(P, dL_dmeans2D, radii, accum, denom, max_radii, (cudaStream_t)stream);
+    return stage_check(false, (cudaStream_t)stream, "densify_stats");
 }
 
 // ---- introspection ---------------------------------------------------------------------------

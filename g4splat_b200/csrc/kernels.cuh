@@ -93,6 +93,8 @@ struct ProjectBwdArgs {
 };
 void launch_project_bwd(const ProjectBwdArgs& a, cudaStream_t s);
 
+void launch_densify_stats(int P, const float* dL_dmeans2D, const int* radii, float* accum, float* denom,
+                          int* max_radii, cudaStream_t s);
 void launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s);
 
 }  // namespace g4s

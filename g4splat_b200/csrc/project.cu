@@ -275,142 +275,175 @@ __device__ __forceinline__ f3 sh_backward(int deg, int M, const float* __restric
                (-v.x * v.z * ddir.x - v.y * v.z * ddir.y + (sum2 - v.z * v.z) * ddir.z) * inv);
 }
 
-// Backward projection: one thread per Gaussian, writes EVERY output element (zeros when the
-// Gaussian was not visible) so the caller never has to clear the gradient tensors.
-__global__ void __launch_bounds__(256) project_bwd_kernel(ProjectBwdArgs a) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= a.P) return;
-    float* dsh = a.dL_dsh ? a.dL_dsh + (size_t)idx * a.M * 3 : nullptr;
-    const bool visible = a.radii[idx] > 0;
-    if (!visible) {
-        for (int i = 0; i < 3; i++) { a.dL_dmeans3D[3 * idx + i] = 0.f; a.dL_dmeans2D[3 * idx + i] = 0.f; a.dL_dcolors[3 * idx + i] = 0.f; }
-        a.dL_dopacity[idx] = 0.f;
-        a.dL_dscales[2 * idx] = 0.f; a.dL_dscales[2 * idx + 1] = 0.f;
-        for (int i = 0; i < 4; i++) a.dL_drots[4 * idx + i] = 0.f;
-        for (int i = 0; i < 9; i++) a.dL_dtransMat[9 * idx + i] = 0.f;
-        if (dsh) for (int i = 0; i < 3 * a.M; i++) dsh[i] = 0.f;
-        return;
-    }
-    // blend-stage accumulators
-    const float4* acc = a.acc + (size_t)idx * ACC_F4;
-    const float4 a0 = acc[0], a1 = acc[1], a2 = acc[2], a3 = acc[3], a4 = acc[4];
-    float dT[3][3] = {{a0.x, a0.y, a0.z}, {a0.w, a1.x, a1.y}, {a1.z, a1.w, a2.x}};  // dT[j] = d/dT row j (Tu,Tv,Tw)
-    const float blend_dT2 = a0.z, blend_dT5 = a1.y;  // proxy inputs (scales path: untouched accumulators)
-    const float m2x = a2.y, m2y = a2.z;
-    const f3 dcol = mk3(a3.x, a3.y, a3.z);
-    const f3 dnrm = mk3(a3.w, a4.x, a4.y);
-    a.dL_dopacity[idx] = a2.w;
-    a.dL_dcolors[3 * idx] = dcol.x; a.dL_dcolors[3 * idx + 1] = dcol.y; a.dL_dcolors[3 * idx + 2] = dcol.z;
+// Backward projection: one thread per Gaussian.  EVERY output element is written (zeros when the
+// Gaussian was not visible) so the caller never has to clear the gradient tensors.  A thread's
+// 73 output floats are staged in shared memory in exactly the global layout of its warp's 32
+// Gaussians, then the warp streams them out with fully coalesced stores (128-bit for the SH
+// block, which is 2/3 of the bytes): a thread-per-Gaussian store would scatter every 4-byte
+// word of a warp over 32 different cache lines.
+constexpr int PB_THREADS = 128;
+constexpr int PB_WARPS = PB_THREADS / 32;
+constexpr int PB_SMALL = 25;      // means3D 3, means2D 3, colors 3, opacity 1, scales 2, rots 4, transMat 9
+constexpr int PB_MAX_M = 16;
+constexpr int PB_SH_STRIDE = PB_MAX_M * 3 + 1;   // odd row stride: conflict-free per-thread writes
 
-    // W, H as the reference rebuilds them in fp32 (CR/backward.cu:618-619)
-    const int Wq = int(a.focal_x * a.tan_fovx * 2);
-    const int Hq = int(a.focal_y * a.tan_fovy * 2);
+__global__ void __launch_bounds__(PB_THREADS) project_bwd_kernel(ProjectBwdArgs a) {
+    __shared__ float s_sh[PB_WARPS][32 * PB_SH_STRIDE];
+    __shared__ float s_small[PB_WARPS][32 * PB_SMALL];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warp_base = (blockIdx.x * PB_WARPS + warp) * 32;   // first Gaussian of this warp
+    if (warp_base >= a.P) return;
+    const int idx = warp_base + lane;
+    const int M = a.M;
+    const bool has_sh_out = a.dL_dsh != nullptr;
+    float* my_sh = &s_sh[warp][lane * PB_SH_STRIDE];
+    float* my = &s_small[warp][lane * PB_SMALL];
+    // slots of `my`: 0-2 means3D, 3-5 means2D, 6-8 colors, 9 opacity, 10-11 scales, 12-15 rots, 16-24 transMat
+#pragma unroll
+    for (int i = 0; i < PB_SMALL; i++) my[i] = 0.f;
+    const bool visible = idx < a.P && a.radii[idx] > 0;
+    // Gaussians without an SH gradient are written as zeros straight from registers below
+    const unsigned sh_rows = __ballot_sync(0xffffffffu, visible && a.shs != nullptr);
+    if (visible) {
+        // blend-stage accumulators
+        const float4* acc = a.acc + (size_t)idx * ACC_F4;
+        const float4 a0 = acc[0], a1 = acc[1], a2 = acc[2], a3 = acc[3], a4 = acc[4];
+        float dT[3][3] = {{a0.x, a0.y, a0.z}, {a0.w, a1.x, a1.y}, {a1.z, a1.w, a2.x}};  // dT[j] = d/d(Tu,Tv,Tw)[j]
+        const float m2x = a2.y, m2y = a2.z;
+        const f3 dcol = mk3(a3.x, a3.y, a3.z);
+        const f3 dnrm = mk3(a3.w, a4.x, a4.y);
+        my[9] = a2.w;
+        my[6] = dcol.x; my[7] = dcol.y; my[8] = dcol.z;
 
-    const float4* rec = a.geom.rec + (size_t)idx * REC_F4;
-    const float4 q1 = rec[1], q2 = rec[2], q3 = rec[3];
-    const bool precomp = (a.scales == nullptr);
-    const f3 p = mk3(a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]);
-    f3 Tu, Tv, Tw, R[3], normal = mk3(0, 0, 0);
-    float sx = 0, sy = 0;
-    float Pm[3][4];
-    float4 quat = make_float4(1, 0, 0, 0);
-    if (precomp) {
-        Tu = mk3(q1.x, q1.y, q1.z); Tv = mk3(q1.w, q2.x, q2.y); Tw = mk3(q2.z, q2.w, q3.x);
-    } else {
-        const float2 sc = ((const float2*)a.scales)[idx];
-        quat = ((const float4*)a.rotations)[idx];
-        sx = sc.x; sy = sc.y;  // scale_modifier ignored on purpose (quirk 2, CR/backward.cu:481)
-        quat_to_R(quat, R);
-        // P = world2ndc * ndc2pix (mat3x4), T = transpose(M) * P (CR/backward.cu:490-504)
-        const float nd[3][4] = {{float(Wq) / 2.0f, 0, 0, float(Wq - 1) / 2.0f},
-                                {0, float(Hq) / 2.0f, 0, float(Hq - 1) / 2.0f},
-                                {0, 0, 0, 1}};
-        const float* pm = a.proj;
+        // W, H as the reference rebuilds them in fp32 (CR/backward.cu:618-619)
+        const int Wq = int(a.focal_x * a.tan_fovx * 2);
+        const int Hq = int(a.focal_y * a.tan_fovy * 2);
+
+        const float4* rec = a.geom.rec + (size_t)idx * REC_F4;
+        const float4 q1 = rec[1], q2 = rec[2], q3 = rec[3];
+        const bool precomp = (a.scales == nullptr);
+        const f3 p = mk3(a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]);
+        f3 Tu, Tv, Tw, R[3], normal = mk3(0, 0, 0);
+        float sx = 0, sy = 0;
+        float Pm[3][4];
+        float4 quat = make_float4(1, 0, 0, 0);
+        if (precomp) {
+            Tu = mk3(q1.x, q1.y, q1.z); Tv = mk3(q1.w, q2.x, q2.y); Tw = mk3(q2.z, q2.w, q3.x);
+        } else {
+            const float2 sc = ((const float2*)a.scales)[idx];
+            quat = ((const float4*)a.rotations)[idx];
+            sx = sc.x; sy = sc.y;  // scale_modifier ignored on purpose (quirk 2, CR/backward.cu:481)
+            quat_to_R(quat, R);
+            // P = world2ndc * ndc2pix (mat3x4), T = transpose(M) * P (CR/backward.cu:490-504)
+            const float nd[3][4] = {{float(Wq) / 2.0f, 0, 0, float(Wq - 1) / 2.0f},
+                                    {0, float(Hq) / 2.0f, 0, float(Hq - 1) / 2.0f},
+                                    {0, 0, 0, 1}};
+            const float* pm = a.proj;
 #pragma unroll
-        for (int c = 0; c < 3; c++)
+            for (int c = 0; c < 3; c++)
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-                Pm[c][k] = pm[0 + 4 * k] * nd[c][0] + pm[1 + 4 * k] * nd[c][1] + pm[2 + 4 * k] * nd[c][2] + pm[3 + 4 * k] * nd[c][3];
-        const f3 L0 = mk3(R[0].x * sx, R[0].y * sx, R[0].z * sx), L1 = mk3(R[1].x * sy, R[1].y * sy, R[1].z * sy);
-        float Tm[3][3];
+                for (int k = 0; k < 4; k++)
+                    Pm[c][k] = pm[0 + 4 * k] * nd[c][0] + pm[1 + 4 * k] * nd[c][1] + pm[2 + 4 * k] * nd[c][2] + pm[3 + 4 * k] * nd[c][3];
+            const f3 L0 = mk3(R[0].x * sx, R[0].y * sx, R[0].z * sx), L1 = mk3(R[1].x * sy, R[1].y * sy, R[1].z * sy);
+            float Tm[3][3];
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-            Tm[c][0] = L0.x * Pm[c][0] + L0.y * Pm[c][1] + L0.z * Pm[c][2];
-            Tm[c][1] = L1.x * Pm[c][0] + L1.y * Pm[c][1] + L1.z * Pm[c][2];
-            Tm[c][2] = p.x * Pm[c][0] + p.y * Pm[c][1] + p.z * Pm[c][2] + Pm[c][3];
+            for (int c = 0; c < 3; c++) {
+                Tm[c][0] = L0.x * Pm[c][0] + L0.y * Pm[c][1] + L0.z * Pm[c][2];
+                Tm[c][1] = L1.x * Pm[c][0] + L1.y * Pm[c][1] + L1.z * Pm[c][2];
+                Tm[c][2] = p.x * Pm[c][0] + p.y * Pm[c][1] + p.z * Pm[c][2] + Pm[c][3];
+            }
+            Tu = mk3(Tm[0][0], Tm[0][1], Tm[0][2]); Tv = mk3(Tm[1][0], Tm[1][1], Tm[1][2]); Tw = mk3(Tm[2][0], Tm[2][1], Tm[2][2]);
+            normal = xform_vec_4x3(R[2], a.view);
         }
-        Tu = mk3(Tm[0][0], Tm[0][1], Tm[0][2]); Tv = mk3(Tm[1][0], Tm[1][1], Tm[1][2]); Tw = mk3(Tm[2][0], Tm[2][1], Tm[2][2]);
-        normal = xform_vec_4x3(R[2], a.view);
-    }
-    // low-pass centre gradient -> dT (CR/backward.cu:515-541; cutoff-1 approximation, quirk 4)
-    if (m2x != 0 || m2y != 0) {
-        const float distance = Tw.x * Tw.x + Tw.y * Tw.y - Tw.z * Tw.z;
-        const float f = 1 / distance;
-        const float dpx_dT00 = f * Tw.x, dpx_dT01 = f * Tw.y, dpx_dT02 = -f * Tw.z;
-        const float dpx_dT30 = Tu.x * (f - 2 * f * f * Tw.x * Tw.x);
-        const float dpx_dT31 = Tu.y * (f - 2 * f * f * Tw.y * Tw.y);
-        const float dpx_dT32 = -Tu.z * (f + 2 * f * f * Tw.z * Tw.z);
-        const float dpy_dT30 = Tv.x * (f - 2 * f * f * Tw.x * Tw.x);
-        const float dpy_dT31 = Tv.y * (f - 2 * f * f * Tw.y * Tw.y);
-        const float dpy_dT32 = -Tv.z * (f + 2 * f * f * Tw.z * Tw.z);
-        dT[0][0] += m2x * dpx_dT00; dT[0][1] += m2x * dpx_dT01; dT[0][2] += m2x * dpx_dT02;
-        dT[1][0] += m2y * dpx_dT00; dT[1][1] += m2y * dpx_dT01; dT[1][2] += m2y * dpx_dT02;
-        dT[2][0] += m2x * dpx_dT30 + m2y * dpy_dT30;
-        dT[2][1] += m2x * dpx_dT31 + m2y * dpy_dT31;
-        dT[2][2] += m2x * dpx_dT32 + m2y * dpy_dT32;
-    }
-    float proxy2, proxy5;
-    if (precomp) {
-        // dL_dtransMat is the gradient of the precomputed input and feeds the proxy after the
-        // update above (CR/backward.cu:542-553)
-        for (int j = 0; j < 3; j++) for (int c = 0; c < 3; c++) a.dL_dtransMat[9 * idx + 3 * j + c] = dT[j][c];
-        proxy2 = dT[0][2]; proxy5 = dT[1][2];
-        for (int i = 0; i < 3; i++) a.dL_dmeans3D[3 * idx + i] = 0.f;
-        a.dL_dscales[2 * idx] = 0.f; a.dL_dscales[2 * idx + 1] = 0.f;
-        for (int i = 0; i < 4; i++) a.dL_drots[4 * idx + i] = 0.f;
-    } else {
-        // the reference returns the raw blend-stage accumulator here
-        a.dL_dtransMat[9 * idx + 0] = a0.x; a.dL_dtransMat[9 * idx + 1] = a0.y; a.dL_dtransMat[9 * idx + 2] = a0.z;
-        a.dL_dtransMat[9 * idx + 3] = a0.w; a.dL_dtransMat[9 * idx + 4] = a1.x; a.dL_dtransMat[9 * idx + 5] = a1.y;
-        a.dL_dtransMat[9 * idx + 6] = a1.z; a.dL_dtransMat[9 * idx + 7] = a1.w; a.dL_dtransMat[9 * idx + 8] = a2.x;
-        proxy2 = blend_dT2; proxy5 = blend_dT5;
-        // dL_dM[c][k] = sum_j P[j][k] * dT[j][c]
-        float dM[3][3];
+        // low-pass centre gradient -> dT (CR/backward.cu:515-541; cutoff-1 approximation, quirk 4)
+        if (m2x != 0 || m2y != 0) {
+            const float distance = Tw.x * Tw.x + Tw.y * Tw.y - Tw.z * Tw.z;
+            const float f = 1 / distance;
+            const float dpx_dT00 = f * Tw.x, dpx_dT01 = f * Tw.y, dpx_dT02 = -f * Tw.z;
+            const float dpx_dT30 = Tu.x * (f - 2 * f * f * Tw.x * Tw.x);
+            const float dpx_dT31 = Tu.y * (f - 2 * f * f * Tw.y * Tw.y);
+            const float dpx_dT32 = -Tu.z * (f + 2 * f * f * Tw.z * Tw.z);
+            const float dpy_dT30 = Tv.x * (f - 2 * f * f * Tw.x * Tw.x);
+            const float dpy_dT31 = Tv.y * (f - 2 * f * f * Tw.y * Tw.y);
+            const float dpy_dT32 = -Tv.z * (f + 2 * f * f * Tw.z * Tw.z);
+            dT[0][0] += m2x * dpx_dT00; dT[0][1] += m2x * dpx_dT01; dT[0][2] += m2x * dpx_dT02;
+            dT[1][0] += m2y * dpx_dT00; dT[1][1] += m2y * dpx_dT01; dT[1][2] += m2y * dpx_dT02;
+            dT[2][0] += m2x * dpx_dT30 + m2y * dpy_dT30;
+            dT[2][1] += m2x * dpx_dT31 + m2y * dpy_dT31;
+            dT[2][2] += m2x * dpx_dT32 + m2y * dpy_dT32;
+        }
+        float proxy2, proxy5;
+        if (precomp) {
+            // dL_dtransMat is the gradient of the precomputed input and feeds the proxy after the
+            // update above (CR/backward.cu:542-553)
+            for (int j = 0; j < 3; j++) for (int c = 0; c < 3; c++) my[16 + 3 * j + c] = dT[j][c];
+            proxy2 = dT[0][2]; proxy5 = dT[1][2];
+        } else {
+            // the reference returns the raw blend-stage accumulator here
+            my[16] = a0.x; my[17] = a0.y; my[18] = a0.z; my[19] = a0.w; my[20] = a1.x; my[21] = a1.y;
+            my[22] = a1.z; my[23] = a1.w; my[24] = a2.x;
+            proxy2 = a0.z; proxy5 = a1.y;
+            // dL_dM[c][k] = sum_j P[j][k] * dT[j][c]
+            float dM[3][3];
 #pragma unroll
-        for (int c = 0; c < 3; c++)
+            for (int c = 0; c < 3; c++)
 #pragma unroll
-            for (int k = 0; k < 3; k++) dM[c][k] = Pm[0][k] * dT[0][c] + Pm[1][k] * dT[1][c] + Pm[2][k] * dT[2][c];
-        f3 dtn = xform_vec_4x3_T(dnrm, a.view);
-        const f3 pv = xform_point_4x3(p, a.view);
-        const float cosv = -sum3(mul3(pv, normal));
-        const float mult = cosv > 0 ? 1.0f : -1.0f;
-        dtn = scale3(mult, dtn);
-        // dL_dR columns: dRS0 * sx, dRS1 * sy, dtn ; quat_to_rotmat_vjp (CR/auxiliary.h:237-281)
-        const f3 v0 = mk3(dM[0][0] * sx, dM[0][1] * sx, dM[0][2] * sx);
-        const f3 v1 = mk3(dM[1][0] * sy, dM[1][1] * sy, dM[1][2] * sy);
-        const f3 v2 = dtn;
-        const float s = rsqrtf(quat.w * quat.w + quat.x * quat.x + quat.y * quat.y + quat.z * quat.z);
-        const float w = quat.x * s, x = quat.y * s, y = quat.z * s, z = quat.w * s;
-        // vR[c][r]: v0 = column 0 (x,y,z = rows 0,1,2) ...
-        const float vR01 = v0.y, vR02 = v0.z, vR00 = v0.x, vR10 = v1.x, vR11 = v1.y, vR12 = v1.z, vR20 = v2.x, vR21 = v2.y, vR22 = v2.z;
-        a.dL_drots[4 * idx + 0] = 2.f * (x * (vR12 - vR21) + y * (vR20 - vR02) + z * (vR01 - vR10));
-        a.dL_drots[4 * idx + 1] = 2.f * (-2.f * x * (vR11 + vR22) + y * (vR01 + vR10) + z * (vR02 + vR20) + w * (vR12 - vR21));
-        a.dL_drots[4 * idx + 2] = 2.f * (x * (vR01 + vR10) - 2.f * y * (vR00 + vR22) + z * (vR12 + vR21) + w * (vR20 - vR02));
-        a.dL_drots[4 * idx + 3] = 2.f * (x * (vR02 + vR20) + y * (vR12 + vR21) - 2.f * z * (vR00 + vR11) + w * (vR01 - vR10));
-        a.dL_dscales[2 * idx] = dM[0][0] * R[0].x + dM[0][1] * R[0].y + dM[0][2] * R[0].z;
-        a.dL_dscales[2 * idx + 1] = dM[1][0] * R[1].x + dM[1][1] * R[1].y + dM[1][2] * R[1].z;
-        a.dL_dmeans3D[3 * idx] = dM[2][0]; a.dL_dmeans3D[3 * idx + 1] = dM[2][1]; a.dL_dmeans3D[3 * idx + 2] = dM[2][2];
+                for (int k = 0; k < 3; k++) dM[c][k] = Pm[0][k] * dT[0][c] + Pm[1][k] * dT[1][c] + Pm[2][k] * dT[2][c];
+            f3 dtn = xform_vec_4x3_T(dnrm, a.view);
+            const f3 pv = xform_point_4x3(p, a.view);
+            const float cosv = -sum3(mul3(pv, normal));
+            const float mult = cosv > 0 ? 1.0f : -1.0f;
+            dtn = scale3(mult, dtn);
+            // dL_dR columns: dRS0 * sx, dRS1 * sy, dtn ; quat_to_rotmat_vjp (CR/auxiliary.h:237-281)
+            const f3 v0 = mk3(dM[0][0] * sx, dM[0][1] * sx, dM[0][2] * sx);
+            const f3 v1 = mk3(dM[1][0] * sy, dM[1][1] * sy, dM[1][2] * sy);
+            const f3 v2 = dtn;
+            const float s = rsqrtf(quat.w * quat.w + quat.x * quat.x + quat.y * quat.y + quat.z * quat.z);
+            const float w = quat.x * s, x = quat.y * s, y = quat.z * s, z = quat.w * s;
+            const float vR00 = v0.x, vR01 = v0.y, vR02 = v0.z, vR10 = v1.x, vR11 = v1.y, vR12 = v1.z, vR20 = v2.x, vR21 = v2.y, vR22 = v2.z;
+            my[12] = 2.f * (x * (vR12 - vR21) + y * (vR20 - vR02) + z * (vR01 - vR10));
+            my[13] = 2.f * (-2.f * x * (vR11 + vR22) + y * (vR01 + vR10) + z * (vR02 + vR20) + w * (vR12 - vR21));
+            my[14] = 2.f * (x * (vR01 + vR10) - 2.f * y * (vR00 + vR22) + z * (vR12 + vR21) + w * (vR20 - vR02));
+            my[15] = 2.f * (x * (vR02 + vR20) + y * (vR12 + vR21) - 2.f * z * (vR00 + vR11) + w * (vR01 - vR10));
+            my[10] = dM[0][0] * R[0].x + dM[0][1] * R[0].y + dM[0][2] * R[0].z;
+            my[11] = dM[1][0] * R[1].x + dM[1][1] * R[1].y + dM[1][2] * R[1].z;
+            my[0] = dM[2][0]; my[1] = dM[2][1]; my[2] = dM[2][2];
+        }
+        if (a.shs) {
+            const f3 dir = sub3(p, mk3(a.campos[0], a.campos[1], a.campos[2]));
+            const f3 dmean = sh_backward(a.D, M, a.shs + (size_t)idx * M * 3, dir, a.geom.clamped[idx], dcol, my_sh);
+            my[0] += dmean.x; my[1] += dmean.y; my[2] += dmean.z;
+        }
+        // densification proxy (CR/backward.cu:637-640, quirk 5): depth = forward T[8]
+        const float depth = q3.x;
+        my[3] = proxy2 * depth * 0.5f * float(Wq);
+        my[4] = proxy5 * depth * 0.5f * float(Hq);
     }
-    if (a.shs) {
-        const f3 dir = sub3(p, mk3(a.campos[0], a.campos[1], a.campos[2]));
-        const f3 dmean = sh_backward(a.D, a.M, a.shs + (size_t)idx * a.M * 3, dir, a.geom.clamped[idx], dcol, dsh);
-        a.dL_dmeans3D[3 * idx] += dmean.x; a.dL_dmeans3D[3 * idx + 1] += dmean.y; a.dL_dmeans3D[3 * idx + 2] += dmean.z;
+    __syncwarp();
+    // ---- coalesced write-out of the warp's 32 Gaussians ---------------------------------------
+    const int nvalid = min(32, a.P - warp_base);
+    auto stream_out = [&](float* dst, int width, int slot) {
+        float* g = dst + (size_t)warp_base * width;
+        for (int e = lane; e < nvalid * width; e += 32) g[e] = s_small[warp][(e / width) * PB_SMALL + slot + (e % width)];
+    };
+    stream_out(a.dL_dmeans3D, 3, 0);
+    stream_out(a.dL_dmeans2D, 3, 3);
+    stream_out(a.dL_dcolors, 3, 6);
+    stream_out(a.dL_dopacity, 1, 9);
+    stream_out(a.dL_dscales, 2, 10);
+    stream_out(a.dL_drots, 4, 12);
+    stream_out(a.dL_dtransMat, 9, 16);
+    if (has_sh_out) {
+        const int row = M * 3;                            // 48 floats per Gaussian at M = 16
+        const int total = nvalid * row;
+        float* g = a.dL_dsh + (size_t)warp_base * row;
+        int i = lane / row, c = lane - i * row;
+        for (int e = lane; e < total; e += 32) {          // every store instruction covers 128 contiguous bytes
+            g[e] = ((sh_rows >> i) & 1u) ? s_sh[warp][i * PB_SH_STRIDE + c] : 0.f;
+            c += 32;
+            while (c >= row) { c -= row; i++; }
+        }
     }
-    // densification proxy (CR/backward.cu:637-640, quirk 5): depth = forward T[8]
-    const float depth = q3.x;
-    a.dL_dmeans2D[3 * idx + 0] = proxy2 * depth * 0.5f * float(Wq);
-    a.dL_dmeans2D[3 * idx + 1] = proxy5 * depth * 0.5f * float(Hq);
-    a.dL_dmeans2D[3 * idx + 2] = 0.f;
 }
 
 __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means3D,
@@ -422,7 +455,30 @@ __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* _
     present[idx] = !(pv.z <= 0.2f);
 }
 
+// Densification bookkeeping the trainer runs after every backward (2DGS/scene/gaussian_model.py:
+// 649-651 add_densification_stats + train_with_refine_depth.py:583 max_radii2D), fused in one pass:
+//   visible = radii > 0;  accum += |dL_dmean2D.xy| on visible;  denom += visible;  max_radii = max(.)
+__global__ void __launch_bounds__(256) densify_stats_kernel(int P, const float* __restrict__ dL_dmeans2D,
+                                                            const int* __restrict__ radii, float* __restrict__ accum,
+                                                            float* __restrict__ denom, int* __restrict__ max_radii) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const int r = radii[idx];
+    if (r > 0) {
+        const float gx = dL_dmeans2D[3 * idx], gy = dL_dmeans2D[3 * idx + 1];
+        accum[idx] += sqrtf(gx * gx + gy * gy);
+        denom[idx] += 1.0f;
+        if (r > max_radii[idx]) max_radii[idx] = r;
+    }
+}
+
 // ---- launchers --------------------------------------------------------------------------------
+void launch_densify_stats(int P, const float* dL_dmeans2D, const int* radii, float* accum, float* denom,
+                          int* max_radii, cudaStream_t s) {
+    if (P <= 0) return;
+    densify_stats_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, dL_dmeans2D, radii, accum, denom, max_radii);
+    count_launch();
+}
 void launch_project_fwd(const ProjectArgs& a, cudaStream_t s) {
     if (a.P <= 0) return;
     project_fwd_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a);
@@ -435,7 +491,7 @@ void launch_scatter(const ScatterArgs& a, cudaStream_t s) {
 }
 void launch_project_bwd(const ProjectBwdArgs& a, cudaStream_t s) {
     if (a.P <= 0) return;
-    project_bwd_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a);
+    project_bwd_kernel<<<(a.P + PB_THREADS - 1) / PB_THREADS, PB_THREADS, 0, s>>>(a);
     count_launch();
 }
 void launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s) {

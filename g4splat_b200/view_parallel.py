@@ -6,16 +6,17 @@ they differentiate the same Gaussian parameters.  So the path shards over VIEWS:
 
   * every rank holds a full replica of the Gaussian parameters;
   * a step's batch of views is split into contiguous blocks, one per rank (`shard_views`);
-  * each rank renders its views forward + backward with the local rasterizer, torch autograd
-    accumulating the parameter gradients over those views;
-  * ONE all-reduce(SUM) of a single flat fp32 buffer carries every parameter gradient plus the
-    two densification statistics the trainer derives from the operator's outputs
-    (`xyz_gradient_accum`, `denom`: 2DGS/scene/gaussian_model.py:649-651), and one
-    all-reduce(MAX) carries `max_radii2D` (train_with_refine_depth.py:583).
+  * each rank renders its views forward + backward with the local rasterizer; autograd
+    accumulates the parameter gradients IN PLACE into one flat fp32 buffer (every `p.grad` is a
+    view of it), which also holds the two densification statistics the trainer derives from
+    the operator's outputs (`xyz_gradient_accum`, `denom`: 2DGS/scene/gaussian_model.py:649-651);
+  * ONE all-reduce(SUM) of that buffer (58 gradient floats + 2 statistics = 240 B per
+    Gaussian) and one all-reduce(MAX) of `max_radii2D` (train_with_refine_depth.py:583) per step.
 
 After `allreduce()` every rank holds gradients identical (up to fp32 summation order) to a
 single-GPU loop over all the views, which is what tests/test_view_parallel.py checks.
-No collective sits on the per-view data path.
+No collective sits on the per-view data path, and nothing is packed or copied for the
+collective: the buffer the kernels accumulate into is the buffer NCCL reduces.
 """
 from __future__ import annotations
 
@@ -34,11 +35,11 @@ def shard_views(num_views: int, world_size: int, rank: int) -> range:
 
 
 class ViewShardedGradSync:
-    """Packs parameter grads + densification statistics into one flat buffer and all-reduces it.
+    """One flat gradient + statistics buffer shared by autograd and the collective.
 
-    params: name -> leaf tensor with requires_grad (e.g. xyz [P,3], features_dc [P,1,3],
-            features_rest [P,15,3], opacity [P,1], scaling [P,2], rotation [P,4]: 58 floats per
-            Gaussian); with the two statistics the buffer is [P, 60] fp32 = 240 B per Gaussian.
+    params: name -> leaf tensor with requires_grad, first dimension P (e.g. xyz [P,3],
+            features [P,16,3], opacity [P,1], scaling [P,2], rotation [P,4]: 58 floats per
+            Gaussian; with the two statistics the buffer holds 60 floats = 240 B per Gaussian).
     """
 
     def __init__(self, params: Dict[str, torch.Tensor], group: Optional[dist.ProcessGroup] = None):
@@ -49,10 +50,27 @@ class ViewShardedGradSync:
         self.device = first.device
         self.sizes = {k: int(v.numel() // max(self.P, 1)) for k, v in params.items()}
         self.width = sum(self.sizes.values()) + 2
-        self.flat = torch.zeros((self.P, self.width), dtype=torch.float32, device=self.device)
+        self.flat = torch.zeros((self.P * self.width,), dtype=torch.float32, device=self.device)
         self.max_radii = torch.zeros((self.P,), dtype=torch.int32, device=self.device)
-        self._stats = self.flat[:, -2:]
+        self._views: Dict[str, torch.Tensor] = {}
+        off = 0
+        for k, p in params.items():
+            n = p.numel()
+            self._views[k] = self.flat[off:off + n].view(p.shape)
+            off += n
+        self._accum = self.flat[off:off + self.P]
+        self._denom = self.flat[off + self.P:off + 2 * self.P]
         self._handles: List = []
+        self._lib = None
+        if self.device.type == "cuda":
+            from . import _lib
+            self._lib = _lib
+        self.attach()
+
+    def attach(self) -> None:
+        """Point every p.grad at its block of the flat buffer so that backward accumulates in place."""
+        for k, p in self.params.items():
+            p.grad = self._views[k]
 
     # -- per view ---------------------------------------------------------------------------
     @torch.no_grad()
@@ -60,69 +78,50 @@ class ViewShardedGradSync:
         """What the trainer does after every backward (train_with_refine_depth.py:582-593,
         gaussian_model.py:649-651): accumulate |dL_dmean2D[:, :2]| and the visibility count of
         visible Gaussians, and the running max of the screen-space radius."""
+        if self._lib is not None and viewspace_grad.is_cuda:
+            g = viewspace_grad.contiguous()
+            r = radii.contiguous()
+            lib = self._lib.load()
+            with torch.cuda.device(self.device):
+                self._lib.check(lib.g4s_densify_stats(self.P, g.data_ptr(), r.data_ptr(), self._accum.data_ptr(),
+                                                      self._denom.data_ptr(), self.max_radii.data_ptr(),
+                                                      torch.cuda.current_stream(self.device).cuda_stream))
+            return
         vis = radii > 0
-        self._stats[:, 0] += torch.where(vis, viewspace_grad[:, :2].norm(dim=-1), torch.zeros((), device=self.device))
-        self._stats[:, 1] += vis.to(torch.float32)
+        self._accum += torch.where(vis, viewspace_grad[:, :2].norm(dim=-1), torch.zeros((), device=self.device))
+        self._denom += vis.to(torch.float32)
         torch.maximum(self.max_radii, radii.to(torch.int32), out=self.max_radii)
 
     def zero(self) -> None:
         self.flat.zero_()
         self.max_radii.zero_()
-        for p in self.params.values():
-            p.grad = None
+        self.attach()
 
     # -- per step ---------------------------------------------------------------------------
-    @torch.no_grad()
-    def pack(self) -> None:
-        col = 0
-        for k, p in self.params.items():
-            n = self.sizes[k]
-            if p.grad is not None:
-                self.flat[:, col:col + n] = p.grad.reshape(self.P, n)
-            else:
-                self.flat[:, col:col + n] = 0
-            col += n
-
-    @torch.no_grad()
-    def unpack(self) -> None:
-        col = 0
-        for k, p in self.params.items():
-            n = self.sizes[k]
-            g = self.flat[:, col:col + n].reshape(p.shape)
-            if p.grad is None:
-                p.grad = g.clone()
-            else:
-                p.grad.copy_(g)
-            col += n
-
     def allreduce(self, async_op: bool = False):
         """SUM over ranks of every gradient + statistic, MAX of the radii.  With async_op the
         collectives run on the process group's stream; call `wait()` before reading grads."""
-        self.pack()
         if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(self.group) == 1:
-            self.unpack()
             return None
         h1 = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
         h2 = dist.all_reduce(self.max_radii, op=dist.ReduceOp.MAX, group=self.group, async_op=async_op)
         if async_op:
             self._handles = [h1, h2]
             return self._handles
-        self.unpack()
         return None
 
     def wait(self) -> None:
         for h in self._handles:
             h.wait()
         self._handles = []
-        self.unpack()
 
     @property
     def xyz_gradient_accum(self) -> torch.Tensor:
-        return self._stats[:, 0:1]
+        return self._accum.view(self.P, 1)
 
     @property
     def denom(self) -> torch.Tensor:
-        return self._stats[:, 1:2]
+        return self._denom.view(self.P, 1)
 
     @property
     def bytes_per_step(self) -> int:
@@ -132,7 +131,7 @@ class ViewShardedGradSync:
 def render_views_sharded(render_one, views: Sequence, sync: ViewShardedGradSync, rank: int, world_size: int,
                          async_allreduce: bool = False):
     """Runs `render_one(view) -> (loss, viewspace_points, radii)` for this rank's block of
-    `views`, back-propagates each loss (grads accumulate in the leaves), records the
+    `views`, back-propagates each loss (grads accumulate in the flat buffer), records the
     densification statistics and all-reduces once.  Returns the local per-view losses."""
     losses = []
     for i in shard_views(len(views), world_size, rank):

@@ -118,6 +118,13 @@ int g4s_backward(int P, int D, int M, int W, int H, const float* background,
 int g4s_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                      uint8_t* present, void* stream);
 
+/* ---- densification statistics (caller-side row "next") ---------------------- */
+/* One fused pass over what the trainer does with the operator's outputs after every backward
+ * (2DGS/scene/gaussian_model.py:649-651 add_densification_stats, train_with_refine_depth.py:583):
+ * for radii[i] > 0:  accum[i] += |dL_dmeans2D[i].xy|, denom[i] += 1, max_radii[i] = max(., radii[i]). */
+int g4s_densify_stats(int P, const float* dL_dmeans2D, const int* radii, float* accum, float* denom,
+                      int* max_radii, void* stream);
+
 /* ---- introspection (tests, benchmarks) ----------------------------------------------------- */
 /* Copies decoded views of the opaque buffers into caller-provided DEVICE arrays (any may be
  * NULL).  Lets stage-level parity tests compare against the oracle without knowing the layout.
