@@ -195,7 +195,7 @@ int g4s_forward_render(int P, int W, int H, const float* background, const void*
 
     BlendFwdArgs ba;
     ba.W = W; ba.H = H; ba.grid_x = gx; ba.grid_y = gy; ba.capacity = capacity;
-    ba.tile_offset = img.tile_offset; ba.tile_order = img.tile_order; ba.list = bin.list; ba.rec = geom.rec;
+    ba.tile_offset = img.tile_offset; ba.tile_order = img.tile_order; ba.list = bin.list; ba.masks = bin.masks; ba.rec = geom.rec;
     ba.bg = background; ba.final_T = img.final_T; ba.n_contrib = img.n_contrib;
     ba.out_color = out_color; ba.out_others = out_others; ba.counters = img.counters;
     { StageTimer tm(ST_BLEND_FWD, s); launch_blend_fwd(ba, s); }
@@ -206,14 +206,14 @@ int g4s_backward(int P, int D, int M, int W, int H, const float* background, con
                  const float* shs, const float* colors_precomp, const float* scales, float scale_modifier,
                  const float* rotations, const float* transMat_precomp, const float* viewmatrix,
                  const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
-                 const int* radii, const void* geom_buffer, const void* binning_buffer,
+                 const int* radii, const void* geom_buffer, const void* binning_buffer, int64_t capacity,
                  const void* img_buffer, const float* dL_dout_color, const float* dL_dout_others,
                  float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors,
                  float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dtransMat,
                  void* scratch, void* stream, int debug) {
     (void)scale_modifier; (void)colors_precomp; (void)transMat_precomp;
     cudaStream_t s = (cudaStream_t)stream;
-    if (P < 0 || W <= 0 || H <= 0) return fail(G4S_EINVAL, "g4s_backward: bad sizes");
+    if (P < 0 || W <= 0 || H <= 0 || capacity < 0) return fail(G4S_EINVAL, "g4s_backward: bad sizes");
     if (P == 0) return G4S_OK;
     if (!geom_buffer || !binning_buffer || !img_buffer || !scratch || !dL_dout_color || !dL_dout_others ||
         !dL_dmeans3D || !dL_dmeans2D || !dL_dcolors || !dL_dopacity || !dL_dscales || !dL_drotations ||
@@ -227,7 +227,7 @@ int g4s_backward(int P, int D, int M, int W, int H, const float* background, con
     BinView bin;
     geom_layout(P, (char*)geom_buffer, &geom);
     image_layout(W, H, (char*)img_buffer, &img);
-    bin_layout(1, (char*)binning_buffer, &bin);  // the sorted list is at offset 0 for every capacity
+    bin_layout(capacity, (char*)binning_buffer, &bin);
     int rc;
     float4* acc = (float4*)scratch;
     {
@@ -238,7 +238,7 @@ int g4s_backward(int P, int D, int M, int W, int H, const float* background, con
     BlendBwdArgs bb;
     bb.W = W; bb.H = H; bb.grid_x = gx; bb.grid_y = gy;
     bb.tile_offset = img.tile_offset; bb.tile_order = img.tile_order;
-    bb.list = bin.list;
+    bb.list = bin.list; bb.masks = bin.masks;
     bb.rec = geom.rec; bb.bg = background; bb.final_T = img.final_T; bb.n_contrib = img.n_contrib;
     bb.dL_dpix = dL_dout_color; bb.dL_dothers = dL_dout_others; bb.acc = acc;
     { StageTimer tm(ST_BLEND_BWD, s); launch_blend_bwd(bb, s); }

@@ -98,20 +98,21 @@ __host__ __device__ inline size_t image_layout(int W, int H, char* base, ImageVi
 
 // Binning buffer (per instance).
 struct BinView {
-    unsigned long long* keys;  // [cap]  depth_bits << 32 | gaussian, bucketed by tile, unsorted
-    uint32_t* list;            // [cap]  gaussian ids, per tile sorted by (depth, id)
+    uint32_t* list;            // [cap]     gaussian ids, per tile sorted by (depth, id)
+    uint32_t* masks;           // [cap][8]  per (instance, warp of the tile): lanes that blended it in the forward
+    unsigned long long* keys;  // [cap]     depth_bits << 32 | gaussian, bucketed by tile, unsorted
 };
 __host__ __device__ inline size_t bin_layout(int64_t cap, char* base, BinView* v) {
     size_t n = (size_t)(cap > 0 ? cap : 1);
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    // the list comes first so that its address does not depend on the capacity (the backward
-    // only needs the list and is not told the capacity)
     size_t o_l = take(n * sizeof(uint32_t));
+    size_t o_m = take(n * 8 * sizeof(uint32_t));
     size_t o_k = take(n * sizeof(unsigned long long));
     if (v) {
-        v->keys = (unsigned long long*)(base + o_k);
         v->list = (uint32_t*)(base + o_l);
+        v->masks = (uint32_t*)(base + o_m);
+        v->keys = (unsigned long long*)(base + o_k);
     }
     return off;
 }

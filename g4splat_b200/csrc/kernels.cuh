@@ -55,6 +55,7 @@ struct BlendFwdArgs {
     const uint32_t* tile_offset;
     const uint32_t* tile_order;
     const uint32_t* list;
+    uint32_t* masks;       // [cap][8] written: lanes of warp w that blended instance i
     const float4* rec;
     const float* bg;
     float* final_T;        // [3][N]
@@ -70,6 +71,7 @@ struct BlendBwdArgs {
     const uint32_t* tile_offset;
     const uint32_t* tile_order;
     const uint32_t* list;
+    const uint32_t* masks;
     const float4* rec;
     const float* bg;
     const float* final_T;

@@ -51,19 +51,36 @@ def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
 
 
 class _CapacityPolicy:
-    """Guess for the number of (Gaussian, tile) instances of the next forward, per device."""
+    """Capacity (number of (Gaussian, tile) instances) to allocate for the next forward, per device.
+
+    Sticky and bucketed: 1.5x the largest count seen recently, rounded up to {1, 1.25, 1.5, 1.75} x 2^k,
+    so that consecutive calls ask the caching allocator for the same block size instead of a new size
+    per view (which fragments the pool and ends in synchronous cudaMalloc calls)."""
 
     def __init__(self):
-        self.last = {}
+        self.cap = {}
+
+    @staticmethod
+    def bucket(n: int) -> int:
+        n = max(int(n), 1 << 16)
+        k = n.bit_length() - 1
+        for q in (4, 5, 6, 7, 8):
+            c = (q << k) >> 2
+            if c >= n:
+                return c
+        return 1 << (k + 1)
 
     def guess(self, dev: int, P: int) -> int:
-        prev = self.last.get(dev)
-        if prev is None:
-            return max(1 << 20, 6 * P)
-        return max(1 << 16, int(prev * 1.5) + 65536)
+        cap = self.cap.get(dev)
+        if cap is None:
+            return self.bucket(max(1 << 20, 6 * P))
+        return cap
 
     def observe(self, dev: int, R: int) -> None:
-        self.last[dev] = R
+        want = self.bucket(int(R * 1.5) + 65536)
+        cur = self.cap.get(dev)
+        if cur is None or want > cur or want * 4 < cur:
+            self.cap[dev] = want
 
 
 _capacity = _CapacityPolicy()
@@ -188,7 +205,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                     _capacity.observe(dev.index or 0, num_rendered)
                     if num_rendered <= cap:
                         break
-                    cap = num_rendered + 65536  # the speculative launch was a no-op: re-issue
+                    cap = _capacity.bucket(num_rendered + 65536)  # the speculative launch was a no-op: re-issue
                 if debug and rs.prefiltered and int(counts[3]) != 0:
                     raise RuntimeError("Point is filtered although prefiltered is set. This shouldn't happen!")
                 ctx.counts = counts
@@ -196,6 +213,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
         ctx.M = M
+        ctx.capacity = cap if P != 0 else 0
         ctx.save_for_backward(colors_c, means3D_c, scales_c, rots_c, cov_c, radii, sh_c, geom, binning, img)
         ctx.mark_non_differentiable(radii)
         return color, radii, others
@@ -234,7 +252,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                     P, int(rs.sh_degree), M, W, H, bg.data_ptr(), _ptr(means3D_c), _ptr(sh_c), _ptr(colors_c),
                     _ptr(scales_c), float(rs.scale_modifier), _ptr(rots_c), _ptr(cov_c), _ptr(view), _ptr(proj),
                     _ptr(campos), float(rs.tanfovx), float(rs.tanfovy), radii.data_ptr(), geom.data_ptr(),
-                    binning.data_ptr(), img.data_ptr(), g_color.data_ptr(), g_others.data_ptr(),
+                    binning.data_ptr(), int(ctx.capacity), img.data_ptr(), g_color.data_ptr(), g_others.data_ptr(),
                     dL_dmeans3D.data_ptr(), dL_dmeans2D.data_ptr(), _ptr(dL_dsh), dL_dcolors.data_ptr(),
                     dL_dopacity.data_ptr(), dL_dscales.data_ptr(), dL_drotations.data_ptr(),
                     dL_dtransMat.data_ptr(), scratch.data_ptr(), sp, int(bool(rs.debug))))

@@ -65,8 +65,8 @@ size_t g4s_geom_bytes(int P);
 /* per-pixel + per-tile state (final T / M1 / M2, last + median contributor, tile counts,
  * offsets): reference ImageState, rasterizer_impl.cu:172-179 */
 size_t g4s_image_bytes(int W, int H);
-/* per-instance state for `capacity` (Gaussian, tile) instances (unsorted 64-bit keys + sorted
- * lists): reference BinningState, rasterizer_impl.cu:181-194 */
+/* per-instance state for `capacity` (Gaussian, tile) instances (sorted lists, per-warp
+ * contribution masks, unsorted 64-bit keys): reference BinningState, rasterizer_impl.cu:181-194 */
 size_t g4s_binning_bytes(int64_t capacity);
 /* backward scratch: per-Gaussian gradient accumulators of the blend stage (the reference's
  * dL_dtransMat / dL_dnormal / dL_dcolors / dL_dmean2D temporaries, rasterize_points.cu:187-195) */
@@ -100,13 +100,15 @@ int g4s_forward_render(int P, int W, int H, const float* background,
  * element is written (zeros for Gaussians that were not visible), callers need not zero them.
  * Outputs (device): dL_dmeans3D[P,3] dL_dmeans2D[P,3] dL_dsh[P,M,3] (may be NULL when M == 0)
  *   dL_dcolors[P,3] dL_dopacity[P] dL_dscales[P,2] dL_drotations[P,4] dL_dtransMat[P,9].
- * scratch: g4s_backward_scratch_bytes(P) bytes. */
+ * scratch: g4s_backward_scratch_bytes(P) bytes.  capacity: the value g4s_forward_render was given
+ * for this binning_buffer. */
 int g4s_backward(int P, int D, int M, int W, int H, const float* background,
                  const float* means3D, const float* shs, const float* colors_precomp,
                  const float* scales, float scale_modifier, const float* rotations,
                  const float* transMat_precomp, const float* viewmatrix, const float* projmatrix,
                  const float* cam_pos, float tan_fovx, float tan_fovy, const int* radii,
-                 const void* geom_buffer, const void* binning_buffer, const void* img_buffer,
+                 const void* geom_buffer, const void* binning_buffer, int64_t capacity,
+                 const void* img_buffer,
                  const float* dL_dout_color, const float* dL_dout_others,
                  float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors,
                  float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dtransMat,

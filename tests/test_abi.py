@@ -43,7 +43,7 @@ def test_version_and_sizes():
     assert lib.g4s_geom_bytes(0) > 0
     n = 1920 * 1080
     assert lib.g4s_image_bytes(1920, 1080) >= n * 20
-    assert lib.g4s_binning_bytes(1 << 20) >= (1 << 20) * 12
+    assert lib.g4s_binning_bytes(1 << 20) >= (1 << 20) * 44
     assert lib.g4s_backward_scratch_bytes(1000) >= 1000 * 80
     assert lib.g4s_launch_count() >= 0
 

@@ -53,11 +53,18 @@ def test_install_registers_the_reference_import_name():
 def test_capacity_policy():
     from g4splat_b200.diff_surfel_rasterization import _CapacityPolicy
     p = _CapacityPolicy()
-    assert p.guess(0, 1_000_000) == 6_000_000
+    assert p.guess(0, 1_000_000) == 6 * (1 << 20)          # first call: 6 P rounded up to a bucket
     assert p.guess(0, 10) == 1 << 20
     p.observe(0, 3_000_000)
-    assert p.guess(0, 1_000_000) == 4_500_000 + 65536
-    assert p.guess(1, 10) == 1 << 20  # per device
+    g = p.guess(0, 1_000_000)
+    assert g >= 4_500_000 + 65536 and g == p.bucket(g)      # 1.5x the count, bucketed
+    p.observe(0, 2_900_000)
+    assert p.guess(0, 1_000_000) == g                        # sticky: similar views reuse the same block size
+    p.observe(0, 9_000_000)
+    assert p.guess(0, 1_000_000) > g                         # grows
+    assert p.guess(1, 10) == 1 << 20                         # per device
+    for n in (1, 65536, 65537, 1_000_000, 5_000_001):
+        assert p.bucket(n) >= n and p.bucket(n) <= max(1 << 16, int(n * 1.26))
 
 
 def bitonic_ascending(keys):
