@@ -300,6 +300,7 @@ def main():
 
     wl = Workload(device, args.views, rank, world)
     sync = ViewShardedGradSync(wl.params)
+    sync.bind(mod)  # B200 operator: kernel-side accumulation into the flat buffer; no-op for the reference
     P, N = wl.P, wl.W * wl.H
     T = ((wl.W + 15) // 16) * ((wl.H + 15) // 16)
 

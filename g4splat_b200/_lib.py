@@ -23,7 +23,7 @@ SIGNATURES = {
                               _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _i]),
     "g4s_forward_render": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i]),
     "g4s_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _f, _f,
-                          _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+                          _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i]),
     "g4s_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
     "g4s_densify_stats": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4s_profile_enable": (_i, [_i]),

@@ -210,7 +210,7 @@ int g4s_backward(int P, int D, int M, int W, int H, const float* background, con
                  const void* img_buffer, const float* dL_dout_color, const float* dL_dout_others,
                  float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors,
                  float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dtransMat,
-                 void* scratch, void* stream, int debug) {
+                 int accumulate_mask, void* scratch, void* stream, int debug) {
     (void)scale_modifier; (void)colors_precomp; (void)transMat_precomp;
     cudaStream_t s = (cudaStream_t)stream;
     if (P < 0 || W <= 0 || H <= 0 || capacity < 0) return fail(G4S_EINVAL, "g4s_backward: bad sizes");
@@ -245,7 +245,7 @@ int g4s_backward(int P, int D, int M, int W, int H, const float* background, con
     if ((rc = stage_check(debug, s, "blend_bwd"))) return rc;
 
     ProjectBwdArgs pb;
-    pb.P = P; pb.D = D; pb.M = M; pb.means3D = means3D; pb.shs = shs; pb.scales = scales; pb.rotations = rotations;
+    pb.P = P; pb.D = D; pb.M = M; pb.accumulate = accumulate_mask; pb.means3D = means3D; pb.shs = shs; pb.scales = scales; pb.rotations = rotations;
     pb.view = viewmatrix; pb.proj = projmatrix; pb.campos = cam_pos;
     pb.focal_y = H / (2.0f * tan_fovy);
     pb.focal_x = W / (2.0f * tan_fovx);

@@ -82,8 +82,10 @@ struct BlendBwdArgs {
 };
 void launch_blend_bwd(const BlendBwdArgs& a, cudaStream_t s);
 
+enum { ACC_MEANS3D = 1, ACC_SH = 2, ACC_OPACITY = 4, ACC_SCALES = 8, ACC_ROTATIONS = 16 };
 struct ProjectBwdArgs {
     int P, D, M;
+    int accumulate;  // ACC_* bits: add into that output (visible rows only) instead of overwriting it
     const float* means3D; const float* shs; const float* scales; const float* rotations;
     const float* view; const float* proj; const float* campos;
     float focal_x, focal_y, tan_fovx, tan_fovy;

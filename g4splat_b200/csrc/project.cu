@@ -421,27 +421,55 @@ __global__ void __launch_bounds__(PB_THREADS) project_bwd_kernel(ProjectBwdArgs 
     }
     __syncwarp();
     // ---- coalesced write-out of the warp's 32 Gaussians ---------------------------------------
+    // accumulate bit set: the destination is a running sum over views (view_parallel's flat gradient
+    // buffer): rows of visible Gaussians are added to, rows of invisible ones are not touched at all.
     const int nvalid = min(32, a.P - warp_base);
-    auto stream_out = [&](float* dst, int width, int slot) {
+    const unsigned vis_rows = __ballot_sync(0xffffffffu, visible);
+    auto stream_out = [&](float* dst, int width, int slot, bool accumulate) {
         float* g = dst + (size_t)warp_base * width;
-        for (int e = lane; e < nvalid * width; e += 32) g[e] = s_small[warp][(e / width) * PB_SMALL + slot + (e % width)];
+        for (int e = lane; e < nvalid * width; e += 32) {
+            const int row = e / width;
+            const float v = s_small[warp][row * PB_SMALL + slot + (e - row * width)];
+            if (!accumulate) g[e] = v;
+            else if ((vis_rows >> row) & 1u) atomicAdd(&g[e], v);  // result unused: fire-and-forget RED
+        }
     };
-    stream_out(a.dL_dmeans3D, 3, 0);
-    stream_out(a.dL_dmeans2D, 3, 3);
-    stream_out(a.dL_dcolors, 3, 6);
-    stream_out(a.dL_dopacity, 1, 9);
-    stream_out(a.dL_dscales, 2, 10);
-    stream_out(a.dL_drots, 4, 12);
-    stream_out(a.dL_dtransMat, 9, 16);
+    stream_out(a.dL_dmeans3D, 3, 0, a.accumulate & ACC_MEANS3D);
+    stream_out(a.dL_dmeans2D, 3, 3, false);
+    stream_out(a.dL_dcolors, 3, 6, false);
+    stream_out(a.dL_dopacity, 1, 9, a.accumulate & ACC_OPACITY);
+    stream_out(a.dL_dscales, 2, 10, a.accumulate & ACC_SCALES);
+    stream_out(a.dL_drots, 4, 12, a.accumulate & ACC_ROTATIONS);
+    stream_out(a.dL_dtransMat, 9, 16, false);
     if (has_sh_out) {
         const int row = M * 3;                            // 48 floats per Gaussian at M = 16
         const int total = nvalid * row;
         float* g = a.dL_dsh + (size_t)warp_base * row;
         int i = lane / row, c = lane - i * row;
-        for (int e = lane; e < total; e += 32) {          // every store instruction covers 128 contiguous bytes
-            g[e] = ((sh_rows >> i) & 1u) ? s_sh[warp][i * PB_SH_STRIDE + c] : 0.f;
-            c += 32;
-            while (c >= row) { c -= row; i++; }
+        const bool acc_sh = a.accumulate & ACC_SH;
+        if (!acc_sh) {
+            for (int e = lane; e < total; e += 32) {      // every store instruction covers 128 contiguous bytes
+                g[e] = ((sh_rows >> i) & 1u) ? s_sh[warp][i * PB_SH_STRIDE + c] : 0.f;
+                c += 32;
+                while (c >= row) { c -= row; i++; }
+            }
+        } else if ((row & 3) == 0) {
+            // running sum over views: only rows with a gradient are touched, 16 bytes per reduction
+            // (the row belongs to this warp alone; RED is used because it does not wait for the load)
+            const int quads = row >> 2;
+            const int nlive = __popc(sh_rows);
+            for (int f = lane; f < nlive * quads; f += 32) {
+                const int k = f / quads, c4 = (f - k * quads) * 4;
+                const int r = __fns(sh_rows, 0, k + 1);   // k-th row with a gradient
+                const float* src = &s_sh[warp][r * PB_SH_STRIDE + c4];
+                atomicAdd(reinterpret_cast<float4*>(g + (size_t)r * row + c4), make_float4(src[0], src[1], src[2], src[3]));
+            }
+        } else {
+            for (int e = lane; e < total; e += 32) {
+                if ((sh_rows >> i) & 1u) atomicAdd(&g[e], s_sh[warp][i * PB_SH_STRIDE + c]);
+                c += 32;
+                while (c >= row) { c -= row; i++; }
+            }
         }
     }
 }

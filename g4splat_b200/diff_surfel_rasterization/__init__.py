@@ -124,6 +124,30 @@ def _check_pending() -> None:
     _pending_overflow[:] = still
 
 
+# ---- opt-in gradient sink (extension; the reference API is unchanged when it is not used) --------
+# Maps the data_ptr of a leaf parameter tensor to the buffer its gradient is accumulated in.  When
+# an input of the operator IS such a parameter, backward adds that view's gradient straight into
+# the buffer inside the kernel (visible rows only) and returns None for it, instead of returning a
+# dense tensor that autograd then adds to `.grad` (view_parallel.ViewShardedGradSync.bind()).
+_grad_sink = {}
+_ACC_BITS = {"means3D": 1, "sh": 2, "opacities": 4, "scales": 8, "rotations": 16}
+
+
+def set_gradient_sink(mapping) -> None:
+    """mapping: {parameter tensor: accumulation buffer of the same shape} (empty / None clears it)."""
+    _grad_sink.clear()
+    for param, buf in (mapping or {}).items():
+        if buf.shape != param.shape or buf.dtype != torch.float32 or not buf.is_contiguous():
+            raise ValueError("gradient sink buffers must be contiguous float32 tensors shaped like their parameter")
+        _grad_sink[(param.data_ptr(), tuple(param.shape))] = buf
+
+
+def _sink_for(t: torch.Tensor):
+    if not _grad_sink or t is None or t.numel() == 0 or not t.requires_grad or not t.is_leaf:
+        return None
+    return _grad_sink.get((t.data_ptr(), tuple(t.shape)))
+
+
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
                         cov3Ds_precomp, raster_settings):
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales,
@@ -210,6 +234,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                     raise RuntimeError("Point is filtered although prefiltered is set. This shouldn't happen!")
                 ctx.counts = counts
 
+        ctx.sinks = {"means3D": _sink_for(means3D), "sh": _sink_for(sh), "opacities": _sink_for(opacities),
+                     "scales": _sink_for(scales), "rotations": _sink_for(rotations)} if _grad_sink else None
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
         ctx.M = M
@@ -228,16 +254,29 @@ class _RasterizeGaussians(torch.autograd.Function):
         H, W = int(rs.image_height), int(rs.image_width)
         f32 = dict(dtype=torch.float32, device=dev)
         alloc = torch.zeros if P == 0 else torch.empty  # every element is written by the kernels
-        dL_dmeans3D = alloc((P, 3), **f32)
+        sinks = ctx.sinks or {}
+        acc_mask = 0
+
+        def out(name, shape):
+            """(tensor handed to the kernel, tensor returned to autograd)"""
+            nonlocal acc_mask
+            buf = sinks.get(name) if P != 0 else None
+            if buf is not None:
+                acc_mask |= _ACC_BITS[name]
+                return buf, None
+            t = alloc(shape, **f32)
+            return t, t
+
+        k_means3D, dL_dmeans3D = out("means3D", (P, 3))
+        k_sh, dL_dsh = out("sh", (P, M, 3))
+        k_opacity, dL_dopacity = out("opacities", (P, 1))
+        k_scales, dL_dscales = out("scales", (P, 2))
+        k_rots, dL_drotations = out("rotations", (P, 4))
         dL_dmeans2D = alloc((P, 3), **f32)
         dL_dcolors = alloc((P, NUM_CHANNELS), **f32)
-        dL_dopacity = alloc((P, 1), **f32)
         dL_dtransMat = alloc((P, 9), **f32)
-        dL_dsh = alloc((P, M, 3), **f32)
-        dL_dscales = alloc((P, 2), **f32)
-        dL_drotations = alloc((P, 4), **f32)
         if P != 0:
-            if M > 0 and sh_c.numel() == 0:
+            if M > 0 and sh_c.numel() == 0 and dL_dsh is not None:
                 dL_dsh.zero_()
             g_color = _f32c(grad_out_color, "dL_dout_color")
             g_others = _f32c(grad_depth, "dL_dout_others")
@@ -253,9 +292,9 @@ class _RasterizeGaussians(torch.autograd.Function):
                     _ptr(scales_c), float(rs.scale_modifier), _ptr(rots_c), _ptr(cov_c), _ptr(view), _ptr(proj),
                     _ptr(campos), float(rs.tanfovx), float(rs.tanfovy), radii.data_ptr(), geom.data_ptr(),
                     binning.data_ptr(), int(ctx.capacity), img.data_ptr(), g_color.data_ptr(), g_others.data_ptr(),
-                    dL_dmeans3D.data_ptr(), dL_dmeans2D.data_ptr(), _ptr(dL_dsh), dL_dcolors.data_ptr(),
-                    dL_dopacity.data_ptr(), dL_dscales.data_ptr(), dL_drotations.data_ptr(),
-                    dL_dtransMat.data_ptr(), scratch.data_ptr(), sp, int(bool(rs.debug))))
+                    k_means3D.data_ptr(), dL_dmeans2D.data_ptr(), _ptr(k_sh), dL_dcolors.data_ptr(),
+                    k_opacity.data_ptr(), k_scales.data_ptr(), k_rots.data_ptr(),
+                    dL_dtransMat.data_ptr(), acc_mask, scratch.data_ptr(), sp, int(bool(rs.debug))))
         # same order as the reference (RAST/diff_surfel_rasterization/__init__.py:144-154)
         return (dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales, dL_drotations,
                 dL_dtransMat, None)

@@ -67,6 +67,16 @@ class ViewShardedGradSync:
             self._lib = _lib
         self.attach()
 
+    def bind(self, op_module, names=None) -> None:
+        """Let the B200 operator add gradients straight into the flat buffer (kernel-side, visible
+        rows only) for parameters that are passed to it as they are; everything else keeps
+        flowing through autograd into the same buffer.  `op_module` must offer set_gradient_sink
+        (g4splat_b200.diff_surfel_rasterization does; the reference extension does not)."""
+        if not hasattr(op_module, "set_gradient_sink"):
+            return
+        names = list(self.params) if names is None else names
+        op_module.set_gradient_sink({self.params[k]: self._views[k] for k in names})
+
     def attach(self) -> None:
         """Point every p.grad at its block of the flat buffer so that backward accumulates in place."""
         for k, p in self.params.items():

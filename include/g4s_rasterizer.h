@@ -101,7 +101,16 @@ int g4s_forward_render(int P, int W, int H, const float* background,
  * Outputs (device): dL_dmeans3D[P,3] dL_dmeans2D[P,3] dL_dsh[P,M,3] (may be NULL when M == 0)
  *   dL_dcolors[P,3] dL_dopacity[P] dL_dscales[P,2] dL_drotations[P,4] dL_dtransMat[P,9].
  * scratch: g4s_backward_scratch_bytes(P) bytes.  capacity: the value g4s_forward_render was given
- * for this binning_buffer. */
+ * for this binning_buffer.
+ * accumulate_mask (0 = reference behaviour): G4S_ACC_* bits select outputs that are running sums
+ * over several views (multi-view steps, view-sharded training): the kernel ADDS the rows of
+ * visible Gaussians into them and does not touch the other rows, which replaces autograd's
+ * dense `grad += new` pass (3 x 232 B per Gaussian at SH degree 3) by a sparse read-modify-write. */
+#define G4S_ACC_MEANS3D 1
+#define G4S_ACC_SH 2
+#define G4S_ACC_OPACITY 4
+#define G4S_ACC_SCALES 8
+#define G4S_ACC_ROTATIONS 16
 int g4s_backward(int P, int D, int M, int W, int H, const float* background,
                  const float* means3D, const float* shs, const float* colors_precomp,
                  const float* scales, float scale_modifier, const float* rotations,
@@ -112,7 +121,7 @@ int g4s_backward(int P, int D, int M, int W, int H, const float* background,
                  const float* dL_dout_color, const float* dL_dout_others,
                  float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors,
                  float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dtransMat,
-                 void* scratch, void* stream, int debug);
+                 int accumulate_mask, void* scratch, void* stream, int debug);
 
 /* ---- markVisible --------------------------------------------------------------------------- */
 /* Replaces Rasterizer::markVisible / checkFrustum (rasterizer_impl.cu:54-66,141-153):

@@ -293,8 +293,10 @@ def test_fused_densification_stats_match_torch():
     assert torch.equal(sync.denom[:, 0], denom) and torch.equal(sync.max_radii, maxr)
 
 
-def test_flat_gradient_buffer_accumulates_in_place(b200, oracle32):
-    """Two views rendered through the operator accumulate into the buffer NCCL would reduce."""
+@pytest.mark.parametrize("bind", [False, True], ids=["autograd", "kernel_sink"])
+def test_flat_gradient_buffer_accumulates_in_place(b200, oracle32, bind):
+    """Two views rendered through the operator accumulate into the buffer NCCL would reduce: through
+    autograd's in-place AccumulateGrad, or (bind) added by the backward kernel itself."""
     import torch
     from g4splat_b200 import synthetic as S
     from g4splat_b200.view_parallel import ViewShardedGradSync
@@ -306,10 +308,11 @@ def test_flat_gradient_buffer_accumulates_in_place(b200, oracle32):
               "rotation": t(sc["rotations"])}
     sync = ViewShardedGradSync(params)
     cams = S.make_cameras(2, case.cam.W, case.cam.H)
-    singles = []
+    singles = [Hh.run_operator(b200, Hh.Case("v", sc, cam, grad_seed=3)) for cam in cams]
+    if bind:
+        sync.bind(b200)
     for cam in cams:
         c2 = Hh.Case("v", sc, cam, grad_seed=3)
-        singles.append(Hh.run_operator(b200, c2))
         rast = b200.GaussianRasterizer(Hh.make_settings(b200, c2, dev))
         m2d = torch.zeros_like(params["xyz"], requires_grad=True)
         color, radii, allmap = rast(means3D=params["xyz"], means2D=m2d, opacities=params["opacity"], shs=params["features"],
@@ -317,6 +320,7 @@ def test_flat_gradient_buffer_accumulates_in_place(b200, oracle32):
         gc, go = c2.upstream()
         torch.autograd.backward([color, allmap], [torch.from_numpy(gc).to(dev), torch.from_numpy(go).to(dev)])
         sync.add_view_stats(m2d.grad, radii)
+    b200.set_gradient_sink(None)
     assert params["xyz"].grad.data_ptr() == sync.flat.data_ptr()  # still the view: accumulated in place
     for name, key in (("xyz", "dL_dmeans3D"), ("features", "dL_dsh"), ("opacity", "dL_dopacity"), ("scaling", "dL_dscales"),
                       ("rotation", "dL_drotations")):
