@@ -100,23 +100,26 @@ constexpr int SORT_SMEM_KEYS = 4096;  // 32 KB of shared memory; longer lists so
 // padding above n never moves, so lists of any length sort in place by skipping hi >= n.
 template <typename KeyArray>
 __device__ __forceinline__ void bitonic_sort_ascending(KeyArray keys, int n) {
-    int m = 1;
-    while (m < n) m <<= 1;
+    int m = 1, log_m = 0;
+    while (m < n) { m <<= 1; log_m++; }
     const int half = m >> 1;
-    for (int k = 2; k <= m; k <<= 1) {
-        const int hk = k >> 1;
+    // all block sizes are powers of two: index arithmetic is shifts and masks, no division
+    for (int lk = 1; lk <= log_m; lk++) {          // k = 1 << lk
+        const int k = 1 << lk, hk = k >> 1;
         for (int i = threadIdx.x; i < half; i += SORT_THREADS) {
-            const int blk = i / hk, within = i - blk * hk;
-            const int lo = blk * k + within, hi = blk * k + k - 1 - within;
+            const int within = i & (hk - 1);
+            const int blk_base = (i >> (lk - 1)) << lk;
+            const int lo = blk_base + within, hi = blk_base + k - 1 - within;
             if (hi < n) {
                 const unsigned long long x = keys[lo], y = keys[hi];
                 if (x > y) { keys[lo] = y; keys[hi] = x; }
             }
         }
         __syncthreads();
-        for (int j = k >> 2; j > 0; j >>= 1) {
+        for (int lj = lk - 2; lj >= 0; lj--) {     // j = 1 << lj
+            const int j = 1 << lj;
             for (int i = threadIdx.x; i < half; i += SORT_THREADS) {
-                const int lo = 2 * j * (i / j) + (i % j), hi = lo + j;
+                const int lo = ((i >> lj) << (lj + 1)) | (i & (j - 1)), hi = lo + j;
                 if (hi < n) {
                     const unsigned long long x = keys[lo], y = keys[hi];
                     if (x > y) { keys[lo] = y; keys[hi] = x; }

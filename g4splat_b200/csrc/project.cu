@@ -211,12 +211,26 @@ __global__ void __launch_bounds__(256) scatter_kernel(ScatterArgs a) {
     const ushort4 r = a.geom.rect[idx];
     const unsigned long long key_hi = ((unsigned long long)__float_as_uint(a.geom.depth[idx])) << 32;
     const unsigned long long key = key_hi | (unsigned long long)(uint32_t)idx;
-    for (int y = r.y; y < r.w; y++)
-        for (int x = r.x; x < r.z; x++) {
-            const int t = y * a.grid_x + x;
-            const uint32_t slot = a.tile_offset[t] + atomicAdd(&a.tile_cursor[t], 1u);
-            a.keys[slot] = key;
+    // four tiles in flight per thread: the cursor atomics return a value, their latency (not their
+    // throughput) bounds a one-at-a-time loop
+    int x = r.x, y = r.y;
+    const int total = (r.z - r.x) * (r.w - r.y);
+    for (int i = 0; i < total; i += 4) {
+        int tile[4];
+        uint32_t slot[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            tile[u] = -1;
+            if (i + u < total) {
+                tile[u] = y * a.grid_x + x;
+                slot[u] = atomicAdd(&a.tile_cursor[tile[u]], 1u);
+                if (++x == r.z) { x = r.x; y++; }
+            }
         }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (tile[u] >= 0) a.keys[a.tile_offset[tile[u]] + slot[u]] = key;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

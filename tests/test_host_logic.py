@@ -71,27 +71,26 @@ def bitonic_ascending(keys):
     """Python mirror of bitonic_sort_ascending (g4splat_b200/csrc/binning.cu): same index math."""
     keys = list(keys)
     n = len(keys)
-    m = 1
+    m, log_m = 1, 0
     while m < n:
         m <<= 1
+        log_m += 1
     half = m >> 1
-    k = 2
-    while k <= m:
-        hk = k >> 1
+    for lk in range(1, log_m + 1):
+        k, hk = 1 << lk, (1 << lk) >> 1
         for i in range(half):
-            blk, within = divmod(i, hk)
-            lo, hi = blk * k + within, blk * k + k - 1 - within
+            within = i & (hk - 1)
+            blk_base = (i >> (lk - 1)) << lk
+            lo, hi = blk_base + within, blk_base + k - 1 - within
             if hi < n and keys[lo] > keys[hi]:
                 keys[lo], keys[hi] = keys[hi], keys[lo]
-        j = k >> 2
-        while j > 0:
+        for lj in range(lk - 2, -1, -1):
+            j = 1 << lj
             for i in range(half):
-                lo = 2 * j * (i // j) + (i % j)
+                lo = ((i >> lj) << (lj + 1)) | (i & (j - 1))
                 hi = lo + j
                 if hi < n and keys[lo] > keys[hi]:
                     keys[lo], keys[hi] = keys[hi], keys[lo]
-            j >>= 1
-        k <<= 1
     return keys
 
 
