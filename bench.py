@@ -104,15 +104,15 @@ class ClockSampler:
 def algorithmic_bytes(stage: str, P: int, V: int, R: int, N: int, T: int, K: int, M: int) -> float:
     """Compulsory bytes per launch of each stage (DESIGN.md 'Kernels'): every input read once,
     every output written once, every (Gaussian, tile) instance written once and read once."""
-    rec = 96 + 4 + 4 + 8 + 1                       # record + depth + ntiles + rect + clamp mask
+    rec = 112 + 4 + 4 + 8 + 1                      # record + depth + ntiles + rect + clamp mask
     return {
         "project_fwd": P * (40 + 4) + V * (12 * K + rec) + R * 4,
         "tile_scan": T * 16,
         "scatter": V * 16 + R * (8 + 4),
         "tile_sort": R * (8 + 4) + T * 8,
-        "blend_fwd": R * (4 + 96) + N * 60 + T * 12,
+        "blend_fwd": R * (4 + 112 + 32) + N * 60 + T * 12,      # list + record gather + contribution masks
         "acc_clear": P * 80,
-        "blend_bwd": R * (4 + 96 + 80) + N * 60 + T * 12,
+        "blend_bwd": R * (4 + 96 + 32 + 80) + N * 60 + T * 12,  # + masks read + accumulator flush
         "project_bwd": P * (4 + 12 + 12 + 4 + 8 + 16 + 36 + 12 + 12 * M) + V * (80 + 96 + 40 + 12 * K),
     }[stage]
 

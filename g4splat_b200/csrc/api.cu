@@ -292,6 +292,7 @@ __global__ void decode_geom_kernel(int P, GeomView geom, float* transMat, float*
     if (normal_opacity) { normal_opacity[4 * i] = q4.x; normal_opacity[4 * i + 1] = q4.y; normal_opacity[4 * i + 2] = q4.z; normal_opacity[4 * i + 3] = q3.w; }
     if (rgb) { rgb[3 * i] = q4.w; rgb[3 * i + 1] = q5.x; rgb[3 * i + 2] = q5.y; }
     if (depths) depths[i] = geom.depth[i];
+    (void)q5;
     if (bbox) { bbox[4 * i] = q0.x; bbox[4 * i + 1] = q0.y; bbox[4 * i + 2] = q0.z; bbox[4 * i + 3] = q0.w; }
     if (clamped) { const uint8_t m = geom.clamped[i]; clamped[3 * i] = m & 1; clamped[3 * i + 1] = (m >> 1) & 1; clamped[3 * i + 2] = (m >> 2) & 1; }
     if (tiles_touched) tiles_touched[i] = geom.ntiles[i];

@@ -19,12 +19,15 @@ constexpr float ALPHA_MIN = 1.0f / 255.0f;
 constexpr float ALPHA_MAX = 0.99f;
 constexpr float T_MIN = 0.0001f;
 
-// ---- projected record: 6 x float4 = 96 B per Gaussian -----------------------------------------
+// ---- projected record: 7 x float4 = 112 B per Gaussian ----------------------------------------
 // q0 = contribution bbox in pixels (xmin, ymin, xmax, ymax): pixels outside can never reach
 //      alpha >= 1/255 for this Gaussian (exact culling, see project.cu)
 // q1 = (Tu.x, Tu.y, Tu.z, Tv.x)   q2 = (Tv.y, Tv.z, Tw.x, Tw.y)   q3 = (Tw.z, cx, cy, opacity)
-// q4 = (nx, ny, nz, r)            q5 = (g, b, depth, 0)
-constexpr int REC_F4 = 6;
+// q4 = (nx, ny, nz, r)            q5 = (g, b, By, rr2)
+// q6 = (Axx, Axy, Ayy, Bx): with By, the contribution ellipse in pixel offsets from (cx, cy),
+//      Axx x^2 + 2 Axy xy + Ayy y^2 + 2 Bx x + 2 By y - 1 <= 0 (all zero: no ellipse test possible);
+//      rr2 = squared radius of the low-pass disc around (cx, cy).  Only the forward reads q6.
+constexpr int REC_F4 = 7;
 constexpr int REC_FLOATS = REC_F4 * 4;
 
 // ---- blend-stage gradient accumulator: 5 x float4 = 80 B per Gaussian -------------------------
@@ -40,7 +43,7 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 
 // Geometry buffer (per Gaussian).  All sections 256-byte aligned.
 struct GeomView {
-    float4* rec;        // [P][6]
+    float4* rec;        // [P][REC_F4]
     float* depth;       // [P]
     uint32_t* ntiles;   // [P] tiles touched after exact culling
     ushort4* rect;      // [P] culled tile rectangle (x0, y0, x1, y1), x1/y1 exclusive
@@ -128,17 +131,67 @@ __device__ __forceinline__ f3 cross3(f3 a, f3 b) {
     return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
 
+// Can a pixel rectangle [rx0,rx1] x [ry0,ry1] (inclusive pixel centres) hold a pixel that reaches
+// alpha >= 1/255 for this splat?  Conservative (never false for a contributing rectangle):
+// the rectangle meets the low-pass disc, or the minimum of the ellipse form over it is <= 0.
+// The form is convex (Axx > 0, det > 0), so the minimum is the unconstrained minimiser when that
+// lies inside, else it lies on one of the four edges (a clamped 1-D parabola each).
+__device__ __forceinline__ bool rect_may_contribute(float cx, float cy, float4 cn, float By, float rr2,
+                                                    float rx0, float ry0, float rx1, float ry1) {
+    const float x0 = rx0 - cx, x1 = rx1 - cx, y0 = ry0 - cy, y1 = ry1 - cy;
+    const float nx = fminf(fmaxf(0.f, x0), x1), ny = fminf(fmaxf(0.f, y0), y1);
+    if (!(nx * nx + ny * ny > rr2)) return true;
+    const float Axx = cn.x, Axy = cn.y, Ayy = cn.z, Bx = cn.w;
+    const float det = Axx * Ayy - Axy * Axy;
+    if (!(Axx > 0.f) || !(Ayy > 0.f) || !(det > 0.f)) return true;   // no usable ellipse: keep
+    const float inv = 1.0f / det;
+    const float xm = (Axy * By - Ayy * Bx) * inv, ym = (Axy * Bx - Axx * By) * inv;
+    if (xm >= x0 && xm <= x1 && ym >= y0 && ym <= y1) return true;
+    auto form = [&](float x, float y) {
+        return x * (Axx * x + 2.f * (Axy * y + Bx)) + y * (Ayy * y + 2.f * By) - 1.f;
+    };
+    const float iyy = 1.0f / Ayy, ixx = 1.0f / Axx;
+    auto cl = [](float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); };
+    float fmin = form(x0, cl(-(Axy * x0 + By) * iyy, y0, y1));
+    fmin = fminf(fmin, form(x1, cl(-(Axy * x1 + By) * iyy, y0, y1)));
+    fmin = fminf(fmin, form(cl(-(Axy * y0 + Bx) * ixx, x0, x1), y0));
+    fmin = fminf(fmin, form(cl(-(Axy * y1 + Bx) * ixx, x0, x1), y1));
+    return !(fmin > 0.f);
+}
+
+// ---- rounding-pinned arithmetic -----------------------------------------------------------------
+// Everything that feeds a hard decision of the reference (alpha >= 1/255, T < 1e-4, T > 0.5,
+// ceil(radius), tile rectangles) is written with explicit _rn intrinsics in the order nvcc's FMA
+// contraction gives the reference's expressions, so that the result does not depend on how this
+// code happens to be inlined or split into basic blocks:
+// The sequences below were read off the SASS / PTX of the reference kernels compiled with the same
+// toolchain (nvcc 12.9, sm_100a): which product of a sum is rounded and which is fused is NOT a
+// fixed rule (it depends on use counts and on ptxas' own mul+add fusion), so each expression names
+// the helper that reproduces its actual sequence:
+//   dot2_rn(a,b,c,d)         fma(a, b, round(c*d))
+//   dot3_rn(a,b,c,d,e,f)     fma(e, f, fma(a, b, round(c*d)))      (second product rounded)
+//   dot3_first_rn(a,...,f)   fma(e, f, fma(c, d, round(a*b)))      (first product rounded)
+//   diff2_rn(a,b,c,d)        fma(a, b, -round(c*d))
+__device__ __forceinline__ float dot2_rn(float a, float b, float c, float d) { return __fmaf_rn(a, b, __fmul_rn(c, d)); }
+__device__ __forceinline__ float dot3_rn(float a, float b, float c, float d, float e, float f) {
+    return __fmaf_rn(e, f, __fmaf_rn(a, b, __fmul_rn(c, d)));
+}
+__device__ __forceinline__ float dot3_first_rn(float a, float b, float c, float d, float e, float f) {
+    return __fmaf_rn(e, f, __fmaf_rn(c, d, __fmul_rn(a, b)));
+}
+__device__ __forceinline__ float diff2_rn(float a, float b, float c, float d) { return __fmaf_rn(a, b, -__fmul_rn(c, d)); }
+
 // view/projection matrices are 16 floats, memory = column-major of the column-vector matrix
 // (CR/auxiliary.h:78-121)
 __device__ __forceinline__ f3 xform_point_4x3(f3 p, const float* m) {
-    return mk3(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12],
-               m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
-               m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14]);
+    return mk3(__fadd_rn(dot3_rn(m[0], p.x, m[4], p.y, m[8], p.z), m[12]),
+               __fadd_rn(dot3_rn(m[1], p.x, m[5], p.y, m[9], p.z), m[13]),
+               __fadd_rn(dot3_rn(m[2], p.x, m[6], p.y, m[10], p.z), m[14]));
 }
 __device__ __forceinline__ f3 xform_vec_4x3(f3 p, const float* m) {
-    return mk3(m[0] * p.x + m[4] * p.y + m[8] * p.z,
-               m[1] * p.x + m[5] * p.y + m[9] * p.z,
-               m[2] * p.x + m[6] * p.y + m[10] * p.z);
+    return mk3(dot3_rn(m[0], p.x, m[4], p.y, m[8], p.z),
+               dot3_rn(m[1], p.x, m[5], p.y, m[9], p.z),
+               dot3_rn(m[2], p.x, m[6], p.y, m[10], p.z));
 }
 __device__ __forceinline__ f3 xform_vec_4x3_T(f3 p, const float* m) {
     return mk3(m[0] * p.x + m[1] * p.y + m[2] * p.z,
@@ -149,11 +202,18 @@ __device__ __forceinline__ f3 xform_vec_4x3_T(f3 p, const float* m) {
 // Rotation matrix of a (w,x,y,z) quaternion, normalised with rsqrtf like the reference
 // (CR/auxiliary.h:212-234).  R[c] = column c.
 __device__ __forceinline__ void quat_to_R(float4 q /* x=w y=x z=y w=z */, f3 R[3]) {
-    float s = rsqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
-    float w = q.x * s, x = q.y * s, y = q.z * s, z = q.w * s;
-    R[0] = mk3(1.f - 2.f * (y * y + z * z), 2.f * (x * y + w * z), 2.f * (x * z - w * y));
-    R[1] = mk3(2.f * (x * y - w * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z + w * x));
-    R[2] = mk3(2.f * (x * z + w * y), 2.f * (y * z - w * x), 1.f - 2.f * (x * x + y * y));
+    // reference SASS: n2 = fma(q2,q2, fma(q1,q1, fma(q0,q0, round(q3*q3))));  the products with w are
+    // rounded and the other product of each pair fused; y*y + z*z is a plain add of rounded squares,
+    // x*x is fused into x*x + z*z and x*x + y*y; 2*() is an exact doubling, 1 - () a plain subtraction.
+    const float n2 = __fmaf_rn(q.z, q.z, __fmaf_rn(q.y, q.y, __fmaf_rn(q.x, q.x, __fmul_rn(q.w, q.w))));
+    const float s = rsqrtf(n2);
+    const float w = __fmul_rn(q.x, s), x = __fmul_rn(q.y, s), y = __fmul_rn(q.z, s), z = __fmul_rn(q.w, s);
+    const float yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+    auto twice = [](float v) { return __fadd_rn(v, v); };
+    const float wz = __fmul_rn(w, z), wy = __fmul_rn(w, y), wx = __fmul_rn(w, x);
+    R[0] = mk3(__fsub_rn(1.f, twice(__fadd_rn(yy, zz))), twice(__fmaf_rn(x, y, wz)), twice(__fmaf_rn(x, z, -wy)));
+    R[1] = mk3(twice(__fmaf_rn(x, y, -wz)), __fsub_rn(1.f, twice(__fmaf_rn(x, x, zz))), twice(__fmaf_rn(y, z, wx)));
+    R[2] = mk3(twice(__fmaf_rn(x, z, wy)), twice(__fmaf_rn(y, z, -wx)), __fsub_rn(1.f, twice(__fmaf_rn(x, x, yy))));
 }
 
 // Tangent-plane -> pixel homography T = (Tu, Tv, Tw) (CR/forward.cu:75-115, glm evaluation order):
@@ -162,14 +222,14 @@ __device__ __forceinline__ void quat_to_R(float4 q /* x=w y=x z=y w=z */, f3 R[3
 // The zero entries of splat2world / ndc2pix contribute exact zeros and are left out.
 __device__ __forceinline__ void build_T(f3 p, float sx, float sy, const f3 R[3], const float* pm,
                                         int W, int H, f3& Tu, f3& Tv, f3& Tw) {
-    f3 L0 = mk3(R[0].x * sx, R[0].y * sx, R[0].z * sx);
-    f3 L1 = mk3(R[1].x * sy, R[1].y * sy, R[1].z * sy);
+    f3 L0 = mk3(__fmul_rn(R[0].x, sx), __fmul_rn(R[0].y, sx), __fmul_rn(R[0].z, sx));
+    f3 L1 = mk3(__fmul_rn(R[1].x, sy), __fmul_rn(R[1].y, sy), __fmul_rn(R[1].z, sy));
     float X[4][3];
 #pragma unroll
     for (int c = 0; c < 4; c++) {
-        X[c][0] = L0.x * pm[c] + L0.y * pm[c + 4] + L0.z * pm[c + 8];
-        X[c][1] = L1.x * pm[c] + L1.y * pm[c + 4] + L1.z * pm[c + 8];
-        X[c][2] = p.x * pm[c] + p.y * pm[c + 4] + p.z * pm[c + 8] + pm[c + 12];
+        X[c][0] = dot3_rn(L0.x, pm[c], L0.y, pm[c + 4], L0.z, pm[c + 8]);
+        X[c][1] = dot3_rn(L1.x, pm[c], L1.y, pm[c + 4], L1.z, pm[c + 8]);
+        X[c][2] = __fadd_rn(dot3_rn(p.x, pm[c], p.y, pm[c + 4], p.z, pm[c + 8]), pm[c + 12]);
     }
     const float hw = float(W) / 2.0f, hw1 = float(W - 1) / 2.0f;
     const float hh = float(H) / 2.0f, hh1 = float(H - 1) / 2.0f;

@@ -70,12 +70,16 @@ __device__ __forceinline__ f3 sh_to_rgb(int deg, const float* __restrict__ sh /*
 //                      that the centre^2 - second-moment cancellation stays small.
 // Returns false when the Gaussian can never contribute (opacity < 1/255).
 __device__ __forceinline__ bool contribution_bbox(f3 Tu, f3 Tv, f3 Tw, float cx, float cy, float opacity,
-                                                  float4& bb) {
+                                                  float4& bb, float4& conic, float& conic_By, float& rr2) {
+    conic = make_float4(0.f, 0.f, 0.f, 0.f);
+    conic_By = 0.f;
+    rr2 = 1e30f;
     if (!(opacity >= ALPHA_MIN)) return false;  // alpha <= opacity < 1/255 for every pixel
     const float rho_cut = 2.0f * logf(255.0f * opacity) * 1.001f + 1e-3f;
     const float big = 1e30f;
     // low-pass disc
     const float rr = sqrtf(0.5f * rho_cut);
+    rr2 = 0.5f * rho_cut * 1.001f + 1e-3f;
     float x0 = -rr, x1 = rr, y0 = -rr, y1 = rr;
     // projected tangent disc, shifted frame: Tu' = Tu - cx Tw, Tv' = Tv - cy Tw
     const f3 U = mk3(Tu.x - cx * Tw.x, Tu.y - cx * Tw.y, Tu.z - cx * Tw.z);
@@ -93,6 +97,24 @@ __device__ __forceinline__ bool contribution_bbox(f3 Tu, f3 Tv, f3 Tw, float cx,
             x0 = fminf(x0, mx - ex); x1 = fmaxf(x1, mx + ex);
             y0 = fminf(y0, my - ey); y1 = fmaxf(y1, my + ey);
             bounded = true;
+            // the same ellipse as a quadratic form in pixel offsets from (cx, cy):
+            // p = x m0 + y m1 + m2 (the homography's adjugate columns), p.x^2 + p.y^2 - rho_cut p.z^2 <= 0
+            const f3 m0 = cross3(V, Tw), m1 = cross3(Tw, U), m2 = cross3(U, V);
+            const float C0 = m2.x * m2.x + m2.y * m2.y - rho_cut * m2.z * m2.z;
+            if (C0 < 0.0f) {
+                const float sc = -1.0f / C0;
+                const float Axx = (m0.x * m0.x + m0.y * m0.y - rho_cut * m0.z * m0.z) * sc;
+                const float Ayy = (m1.x * m1.x + m1.y * m1.y - rho_cut * m1.z * m1.z) * sc;
+                const float Axy = (m0.x * m1.x + m0.y * m1.y - rho_cut * m0.z * m1.z) * sc;
+                const float Bx = (m0.x * m2.x + m0.y * m2.y - rho_cut * m0.z * m2.z) * sc;
+                const float By = (m1.x * m2.x + m1.y * m2.y - rho_cut * m1.z * m2.z) * sc;
+                const bool finite = fabsf(Axx) < 1e30f && fabsf(Ayy) < 1e30f && fabsf(Axy) < 1e30f &&
+                                    fabsf(Bx) < 1e30f && fabsf(By) < 1e30f;
+                if (finite && Axx > 0.0f && Ayy > 0.0f && Axx * Ayy - Axy * Axy > 0.0f) {
+                    conic = make_float4(Axx, Axy, Ayy, Bx);
+                    conic_By = By;
+                }
+            }
         }
     }
     if (!bounded) { bb = make_float4(-big, -big, big, big); return true; }
@@ -102,17 +124,21 @@ __device__ __forceinline__ bool contribution_bbox(f3 Tu, f3 Tv, f3 Tw, float cx,
     return true;
 }
 
-__global__ void __launch_bounds__(256) project_fwd_kernel(ProjectArgs a) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= a.P) return;
-    a.radii[idx] = 0;
-    a.geom.ntiles[idx] = 0;
-
+// Per-thread part of the forward projection.  Returns false when the Gaussian is culled (radii 0).
+struct ProjOut {
+    f3 Tu, Tv, Tw, normal, rgb;
+    float cx, cy, opacity, depth;
+    float4 bb, conic;
+    float conic_By, rr2;
+    int radius, rx0, ry0, rx1, ry1;   // candidate tile rectangle: reference rect x contribution bbox (may be empty)
+    uint8_t clamp_mask;
+};
+__device__ __forceinline__ bool project_one(const ProjectArgs& a, int idx, ProjOut& o) {
     const f3 p = mk3(a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]);
     const f3 pv = xform_point_4x3(p, a.view);
     if (pv.z <= 0.2f) {  // in_frustum (CR/auxiliary.h:199)
         if (a.prefiltered) atomicAdd(&a.counters[CNT_PREFILTER_VIOLATION], 1);
-        return;
+        return false;
     }
     f3 Tu, Tv, Tw, normal;
     if (a.transMat_precomp == nullptr) {
@@ -120,7 +146,7 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(ProjectArgs a) {
         const float4 q = ((const float4*)a.rotations)[idx];
         f3 R[3];
         quat_to_R(q, R);
-        build_T(p, a.scale_modifier * sc.x, a.scale_modifier * sc.y, R, a.proj, a.W, a.H, Tu, Tv, Tw);
+        build_T(p, __fmul_rn(a.scale_modifier, sc.x), __fmul_rn(a.scale_modifier, sc.y), R, a.proj, a.W, a.H, Tu, Tv, Tw);
         normal = xform_vec_4x3(R[2], a.view);
     } else {
         const float* t = a.transMat_precomp + 9 * (size_t)idx;
@@ -128,22 +154,27 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(ProjectArgs a) {
         normal = mk3(0.0f, 0.0f, 1.0f);
     }
     // dual-visible flip (CR/forward.cu:211-216)
-    const float cosv = -sum3(mul3(pv, normal));
-    if (cosv == 0) return;
+    const float cosv = -dot3_rn(pv.x, normal.x, pv.y, normal.y, pv.z, normal.z);
+    if (cosv == 0) return false;
     const float mult = cosv > 0 ? 1.0f : -1.0f;
-    normal = scale3(mult, normal);
+    normal = mk3(__fmul_rn(mult, normal.x), __fmul_rn(mult, normal.y), __fmul_rn(mult, normal.z));
 
-    // 3-sigma AABB: centre + radius exactly as the reference (CR/forward.cu:119-147, :222-233)
-    const f3 tp = mk3(9.0f, 9.0f, -1.0f);
-    const float dist = sum3(mul3(mul3(Tw, Tw), tp));
-    const f3 f = scale3(1 / dist, tp);
-    if (dist == 0.0f) return;
-    const float cx = sum3(mul3(mul3(f, Tu), Tw));
-    const float cy = sum3(mul3(mul3(f, Tv), Tw));
-    const float t0 = sum3(mul3(mul3(f, Tu), Tu));
-    const float t1 = sum3(mul3(mul3(f, Tv), Tv));
-    const float ex = sqrtf(fmaxf(1e-4f, cx * cx - t0));
-    const float ey = sqrtf(fmaxf(1e-4f, cy * cy - t1));
+    // 3-sigma AABB: centre + radius exactly as the reference (CR/forward.cu:119-147, :222-233).
+    // radius = ceil() of a cancelling difference: rounding points pinned to the reference's SASS
+    // (dist = fma(-Tw.z, Tw.z, fma(Tw.x^2, 9, round(Tw.y^2 * 9))); sums round their FIRST product).
+    const float tw2x = __fmul_rn(Tw.x, Tw.x), tw2y = __fmul_rn(Tw.y, Tw.y);
+    const float dist = __fmaf_rn(-Tw.z, Tw.z, __fmaf_rn(tw2x, 9.0f, __fmul_rn(tw2y, 9.0f)));
+    const float inv_dist = __frcp_rn(dist);
+    if (dist == 0.0f) return false;
+    const float f9 = __fmul_rn(inv_dist, 9.0f);
+    const f3 fu = mk3(__fmul_rn(f9, Tu.x), __fmul_rn(f9, Tu.y), __fmul_rn(inv_dist, -Tu.z));
+    const f3 fv = mk3(__fmul_rn(f9, Tv.x), __fmul_rn(f9, Tv.y), __fmul_rn(inv_dist, -Tv.z));
+    const float cx = dot3_first_rn(fu.x, Tw.x, fu.y, Tw.y, fu.z, Tw.z);
+    const float cy = dot3_first_rn(fv.x, Tw.x, fv.y, Tw.y, fv.z, Tw.z);
+    const float t0 = dot3_first_rn(fu.x, Tu.x, fu.y, Tu.y, fu.z, Tu.z);
+    const float t1 = dot3_first_rn(fv.x, Tv.x, fv.y, Tv.y, fv.z, Tv.z);
+    const float ex = sqrtf(fmaxf(1e-4f, __fmaf_rn(cx, cx, -t0)));
+    const float ey = sqrtf(fmaxf(1e-4f, __fmaf_rn(cy, cy, -t1)));
     const float radius = ceilf(fmaxf(ex, ey));
 
     // getRect (CR/auxiliary.h:66-76)
@@ -153,83 +184,120 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(ProjectArgs a) {
     int ry0 = min(gy, max(0, (int)((cy - max_radius) / TILE)));
     int rx1 = min(gx, max(0, (int)((cx + max_radius + TILE - 1) / TILE)));
     int ry1 = min(gy, max(0, (int)((cy + max_radius + TILE - 1) / TILE)));
-    if ((rx1 - rx0) * (ry1 - ry0) == 0) return;
+    if ((rx1 - rx0) * (ry1 - ry0) == 0) return false;
 
     // colour
-    f3 rgb;
-    uint8_t clamp_mask = 0;
+    o.clamp_mask = 0;
     if (a.colors_precomp == nullptr) {
         f3 dir = sub3(p, mk3(a.campos[0], a.campos[1], a.campos[2]));
         const float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
         dir = mk3(dir.x / len, dir.y / len, dir.z / len);
-        rgb = sh_to_rgb(a.D, a.shs + (size_t)idx * a.M * 3, dir, clamp_mask);
+        o.rgb = sh_to_rgb(a.D, a.shs + (size_t)idx * a.M * 3, dir, o.clamp_mask);
     } else {
-        rgb = mk3(a.colors_precomp[3 * idx], a.colors_precomp[3 * idx + 1], a.colors_precomp[3 * idx + 2]);
+        o.rgb = mk3(a.colors_precomp[3 * idx], a.colors_precomp[3 * idx + 1], a.colors_precomp[3 * idx + 2]);
     }
-    const float opacity = a.opacities[idx];
+    o.opacity = a.opacities[idx];
 
-    // exact culling: tiles of the reference rectangle that hold at least one pixel of the
-    // contribution bbox
-    float4 bb;
-    int nt = 0;
-    const bool can_contribute = contribution_bbox(Tu, Tv, Tw, cx, cy, opacity, bb);
+    // exact culling, step 1: tiles of the reference rectangle that hold a pixel of the contribution bbox
+    const bool can_contribute = contribution_bbox(Tu, Tv, Tw, cx, cy, o.opacity, o.bb, o.conic, o.conic_By, o.rr2);
     if (can_contribute) {
         // tile t covers pixels [16 t, 16 t + 15]
-        const float fx0 = fmaxf(ceilf((bb.x - (TILE - 1)) / TILE), (float)rx0);
-        const float fy0 = fmaxf(ceilf((bb.y - (TILE - 1)) / TILE), (float)ry0);
-        const float fx1 = fminf(floorf(bb.z / TILE) + 1.0f, (float)rx1);
-        const float fy1 = fminf(floorf(bb.w / TILE) + 1.0f, (float)ry1);
+        const float fx0 = fmaxf(ceilf((o.bb.x - (TILE - 1)) / TILE), (float)rx0);
+        const float fy0 = fmaxf(ceilf((o.bb.y - (TILE - 1)) / TILE), (float)ry0);
+        const float fx1 = fminf(floorf(o.bb.z / TILE) + 1.0f, (float)rx1);
+        const float fy1 = fminf(floorf(o.bb.w / TILE) + 1.0f, (float)ry1);
         rx0 = (int)fx0; ry0 = (int)fy0; rx1 = (int)fx1; ry1 = (int)fy1;
-        if (rx1 > rx0 && ry1 > ry0) nt = (rx1 - rx0) * (ry1 - ry0);
     }
-    if (nt == 0) { rx0 = ry0 = rx1 = ry1 = 0; bb = make_float4(1e30f, 1e30f, -1e30f, -1e30f); }
+    if (!can_contribute || rx1 <= rx0 || ry1 <= ry0) { rx0 = ry0 = rx1 = ry1 = 0; }
+    o.Tu = Tu; o.Tv = Tv; o.Tw = Tw; o.normal = normal;
+    o.cx = cx; o.cy = cy; o.depth = pv.z; o.radius = max_radius;
+    o.rx0 = rx0; o.ry0 = ry0; o.rx1 = rx1; o.ry1 = ry1;
+    return true;
+}
 
-    a.radii[idx] = max_radius;
+// Forward projection.  One thread per Gaussian for the arithmetic; the per-tile work (exact
+// ellipse-vs-tile test, per-tile counters) is then done warp-cooperatively: for each visible
+// Gaussian of the warp in turn, the 32 lanes take 32 tiles of its rectangle, so long rectangles
+// (close-up splats cover thousands of tiles) do not serialise on one thread, and the surviving-
+// tile mask of small rectangles is simply the ballot.
+__global__ void __launch_bounds__(256) project_fwd_kernel(ProjectArgs a) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    ProjOut o;
+    o.rx0 = o.ry0 = o.rx1 = o.ry1 = 0;
+    const bool visible = idx < a.P && project_one(a, idx, o);
+    const int gx = a.grid_x;
+    const int my_w = o.rx1 - o.rx0, my_total = visible ? my_w * (o.ry1 - o.ry0) : 0;
+    // per-tile counters.  Rectangles of up to 32 tiles are counted by their own lane (fire-and-forget
+    // reductions); longer ones (close-up splats cover thousands of tiles) by the whole warp.
+    // (An exact ellipse-vs-tile test here was measured: it removes ~12 % of the instances of this
+    // workload but costs more in this kernel than it saves downstream; the blend kernel applies the
+    // same test per 8x4 region, where it is nearly free.)
+    constexpr int SERIAL_TILES = 32;
+    const int my_nt = my_total;
+    if (my_total > 0 && my_total <= SERIAL_TILES) {
+        for (int y = o.ry0; y < o.ry1; y++)
+            for (int x = o.rx0; x < o.rx1; x++) atomicAdd(&a.tile_count[y * gx + x], 1u);
+    }
+    unsigned pending = __ballot_sync(0xffffffffu, my_total > SERIAL_TILES);
+    while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1;
+        const int rx0 = __shfl_sync(0xffffffffu, o.rx0, src), ry0 = __shfl_sync(0xffffffffu, o.ry0, src);
+        const int w = __shfl_sync(0xffffffffu, my_w, src), total = __shfl_sync(0xffffffffu, my_total, src);
+        for (int i = lane; i < total; i += 32) {
+            const int iy = i / w, ix = i - iy * w;
+            atomicAdd(&a.tile_count[(ry0 + iy) * gx + rx0 + ix], 1u);
+        }
+    }
+    if (idx >= a.P) return;
+    a.radii[idx] = visible ? o.radius : 0;
+    a.geom.ntiles[idx] = (uint32_t)my_nt;
+    if (!visible) return;
+    if (my_nt == 0) { o.rx0 = o.ry0 = o.rx1 = o.ry1 = 0; o.bb = make_float4(1e30f, 1e30f, -1e30f, -1e30f); }
     float4* rec = a.geom.rec + (size_t)idx * REC_F4;
-    rec[0] = bb;
-    rec[1] = make_float4(Tu.x, Tu.y, Tu.z, Tv.x);
-    rec[2] = make_float4(Tv.y, Tv.z, Tw.x, Tw.y);
-    rec[3] = make_float4(Tw.z, cx, cy, opacity);
-    rec[4] = make_float4(normal.x, normal.y, normal.z, rgb.x);
-    rec[5] = make_float4(rgb.y, rgb.z, pv.z, 0.0f);
-    a.geom.depth[idx] = pv.z;
-    a.geom.clamped[idx] = clamp_mask;
-    a.geom.ntiles[idx] = (uint32_t)nt;
-    a.geom.rect[idx] = make_ushort4((unsigned short)rx0, (unsigned short)ry0, (unsigned short)rx1, (unsigned short)ry1);
+    rec[0] = o.bb;
+    rec[1] = make_float4(o.Tu.x, o.Tu.y, o.Tu.z, o.Tv.x);
+    rec[2] = make_float4(o.Tv.y, o.Tv.z, o.Tw.x, o.Tw.y);
+    rec[3] = make_float4(o.Tw.z, o.cx, o.cy, o.opacity);
+    rec[4] = make_float4(o.normal.x, o.normal.y, o.normal.z, o.rgb.x);
+    rec[5] = make_float4(o.rgb.y, o.rgb.z, o.conic_By, o.rr2);
+    rec[6] = o.conic;
+    a.geom.depth[idx] = o.depth;
+    a.geom.clamped[idx] = o.clamp_mask;
+    a.geom.rect[idx] = make_ushort4((unsigned short)o.rx0, (unsigned short)o.ry0, (unsigned short)o.rx1, (unsigned short)o.ry1);
     atomicAdd(&a.counters[CNT_VISIBLE], 1);
-    for (int y = ry0; y < ry1; y++)
-        for (int x = rx0; x < rx1; x++) atomicAdd(&a.tile_count[y * gx + x], 1u);
 }
 
 // One (Gaussian, tile) instance per surviving tile: key = depth bits << 32 | Gaussian id, written
 // to an arbitrary free slot of the tile's bucket; the per-tile sort orders the bucket afterwards.
+// Warp-cooperative like the counting above: the lanes take the tiles of one Gaussian at a time,
+// so 32 cursor atomics (which return a value) are in flight instead of one.
 __global__ void __launch_bounds__(256) scatter_kernel(ScatterArgs a) {
     if ((int64_t)a.counters[CNT_RENDERED] > a.capacity) return;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= a.P) return;
-    if (a.geom.ntiles[idx] == 0) return;
-    const ushort4 r = a.geom.rect[idx];
-    const unsigned long long key_hi = ((unsigned long long)__float_as_uint(a.geom.depth[idx])) << 32;
-    const unsigned long long key = key_hi | (unsigned long long)(uint32_t)idx;
-    // four tiles in flight per thread: the cursor atomics return a value, their latency (not their
-    // throughput) bounds a one-at-a-time loop
-    int x = r.x, y = r.y;
-    const int total = (r.z - r.x) * (r.w - r.y);
-    for (int i = 0; i < total; i += 4) {
-        int tile[4];
-        uint32_t slot[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            tile[u] = -1;
-            if (i + u < total) {
-                tile[u] = y * a.grid_x + x;
-                slot[u] = atomicAdd(&a.tile_cursor[tile[u]], 1u);
-                if (++x == r.z) { x = r.x; y++; }
-            }
+    const int lane = threadIdx.x & 31;
+    const bool live = idx < a.P && a.geom.ntiles[idx] != 0;
+    ushort4 r = make_ushort4(0, 0, 0, 0);
+    unsigned long long key = 0ull;
+    if (live) {
+        r = a.geom.rect[idx];
+        key = (((unsigned long long)__float_as_uint(a.geom.depth[idx])) << 32) | (unsigned long long)(uint32_t)idx;
+    }
+    const int my_w = r.z - r.x, my_total = my_w * (r.w - r.y);
+    unsigned pending = __ballot_sync(0xffffffffu, live);
+    while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1;
+        const int rx0 = __shfl_sync(0xffffffffu, (int)r.x, src), ry0 = __shfl_sync(0xffffffffu, (int)r.y, src);
+        const int w = __shfl_sync(0xffffffffu, my_w, src), total = __shfl_sync(0xffffffffu, my_total, src);
+        const unsigned long long k = __shfl_sync(0xffffffffu, key, src);
+        for (int i = lane; i < total; i += 32) {
+            const int iy = i / w, ix = i - iy * w;
+            const int t = (ry0 + iy) * a.grid_x + rx0 + ix;
+            const uint32_t slot = a.tile_offset[t] + atomicAdd(&a.tile_cursor[t], 1u);
+            a.keys[slot] = k;
         }
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-            if (tile[u] >= 0) a.keys[a.tile_offset[tile[u]] + slot[u]] = key;
     }
 }
 
