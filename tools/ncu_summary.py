@@ -66,6 +66,37 @@ def full(tag, out):
         out.append("")
 
 
+STAGE_OF = {"project_fwd_kernel": "project_fwd", "tile_scan_kernel": "tile_scan", "scatter_kernel": "scatter",
+            "tile_sort_kernel": "tile_sort", "blend_fwd_kernel": "blend_fwd", "blend_fwd_tma_kernel": "blend_fwd",
+            "blend_bwd_kernel": "blend_bwd", "project_bwd_kernel": "project_bwd"}
+
+
+def traffic(tag):
+    """profiles/traffic.json: measured DRAM bytes (read + write) per launch of each stage, for bench.py's roofline.traffic."""
+    import json
+    p = ROOT / "gpurun_out" / f"{tag}_prof.ncu-rep"
+    if not p.exists():
+        return
+    raw = subprocess.run(["ncu", "-i", str(p), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    acc = {}
+    for r in rows[2:]:
+        name = r[idx["Kernel Name"]].split("(")[0].split("::")[-1]
+        st = STAGE_OF.get(name)
+        if st is None:
+            continue
+        b = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            b += float(r[idx[k]].replace(",", "")) * mult.get(units[idx[k]], 1.0)
+        acc.setdefault(st, []).append(b)
+    out = {k: sum(v) / len(v) for k, v in acc.items()}
+    out["_source"] = f"{p.name}: ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, mean over captured launches"
+    (ROOT / "profiles" / "traffic.json").write_text(json.dumps(out, indent=1))
+
+
 def main():
     tag = sys.argv[1]
     out = [f"# ncu summary {tag}\n", "Workload: `python bench.py --steps 2 --warmup 3 --views 2 --no-cpu-baseline` "
@@ -75,6 +106,7 @@ def main():
     full(tag, out)
     dst = ROOT / "profiles" / f"{tag}_ncu_summary.md"
     dst.write_text("\n".join(out) + "\n")
+    traffic(tag)
     print("wrote", dst)
 
 
