@@ -332,3 +332,75 @@ def test_flat_gradient_buffer_accumulates_in_place(b200, oracle32, bind):
         r = Hh.parity(params[name].grad.cpu().numpy(), want, 1e-4)
         assert r["bad_frac"] == 0, (name, r)
     assert float(sync.denom.sum()) == float(sum((s["radii"] > 0).sum() for s in singles))
+
+
+def _dense_case(P, W, H, seed, scale_mul, opacity):
+    """Every Gaussian in front of the camera, large enough to overlap most of a small image: tile
+    lists far longer than one staging batch / the shared-memory sort capacity."""
+    from g4splat_b200 import synthetic as S
+    rng = np.random.default_rng(seed)
+    cam = S.look_at_camera([0.0, 0.0, -2.0], [0.0, 0.0, 0.0], W, H, 60.0)
+    sc = S.make_scene(P, seed)
+    sc["means3D"] = np.float32(rng.uniform([-0.8, -0.5, -0.3], [0.8, 0.5, 1.5], size=(P, 3)))
+    sc["scales"] = np.float32(sc["scales"] * 0 + scale_mul * np.exp(rng.normal(scale=0.3, size=(P, 2))))
+    sc["opacities"] = np.float32(np.full((P, 1), opacity))
+    return Hh.Case("dense", sc, cam, grad_seed=seed)
+
+
+def test_long_tile_lists_global_sort_fallback(b200, reference, oracle32):
+    """14000 low-opacity splats covering a 64x48 image: every tile list holds thousands of entries
+    (> 4096 = the shared-memory sort capacity, > 256 = many staging batches, rectangles > 32 tiles
+    = the warp-cooperative counting path).  Must still match the reference bit for bit."""
+    case = _dense_case(14000, 64, 48, 41, 0.25, 0.03)
+    want = Hh.run_operator(reference, case)
+    got = Hh.run_operator(b200, case)
+    assert int(b200.last_counts["max_tile_list"]) > 4096, b200.last_counts
+    assert Hh.radii_mismatch(got["radii"], want["radii"]) == 0
+    assert np.array_equal(got["allmap"], want["allmap"])
+    Hh.assert_parity(got, want, ("color",), rtol=1e-6, what="dense forward vs reference")
+    Hh.assert_parity(got, want, Hh.GRAD_KEYS, rtol=1e-4, max_bad_frac=GRAD_BUDGET, what="dense backward vs reference")
+
+
+def test_saturating_splats_early_termination(b200, reference):
+    """Opaque splats: pixels saturate (T < 1e-4) after a few entries, warps and whole tiles stop early;
+    the contribution masks of entries that were never visited must not be consulted."""
+    case = _dense_case(3000, 96, 64, 42, 0.15, 0.95)
+    want = Hh.run_operator(reference, case)
+    got = Hh.run_operator(b200, case)
+    assert np.array_equal(got["allmap"], want["allmap"]) and Hh.radii_mismatch(got["radii"], want["radii"]) == 0
+    Hh.assert_parity(got, want, Hh.GRAD_KEYS, rtol=1e-4, max_bad_frac=GRAD_BUDGET, what="saturating backward vs reference")
+
+
+def test_non_default_stream_and_interleaved_views(b200, oracle32):
+    """Launches follow torch's current stream; two forwards may be outstanding before their backwards
+    (each autograd node owns its scratch buffers)."""
+    import torch
+    from g4splat_b200 import synthetic as S
+    case = Hh.named_case("tiny", oracle32)
+    base = Hh.run_operator(b200, case)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        other = Hh.run_operator(b200, case)
+    side.synchronize()
+    for k in ("color", "allmap", "radii"):
+        assert np.array_equal(base[k], other[k]), k
+    # interleave: fwd(view A), fwd(view B), bwd(B), bwd(A)
+    dev = "cuda"
+    sc = case.scene
+    t = lambda a: torch.from_numpy(a).to(dev).requires_grad_(True)
+    p = {k: t(sc[k]) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    cams = S.make_cameras(2, case.cam.W, case.cam.H)
+    outs, singles = [], []
+    for cam in cams:
+        c2 = Hh.Case("v", sc, cam, grad_seed=5)
+        singles.append(Hh.run_operator(b200, c2))
+        rast = b200.GaussianRasterizer(Hh.make_settings(b200, c2, dev))
+        m2d = torch.zeros_like(p["means3D"], requires_grad=True)
+        outs.append((rast(means3D=p["means3D"], means2D=m2d, opacities=p["opacities"], shs=p["shs"], scales=p["scales"],
+                          rotations=p["rotations"]), c2))
+    for (color, radii, allmap), c2 in reversed(outs):
+        gc, go = c2.upstream()
+        torch.autograd.backward([color, allmap], [torch.from_numpy(gc).to(dev), torch.from_numpy(go).to(dev)])
+    want = singles[0]["dL_dmeans3D"] + singles[1]["dL_dmeans3D"]
+    r = Hh.parity(p["means3D"].grad.cpu().numpy(), want, 1e-4)
+    assert r["bad_frac"] == 0, r
