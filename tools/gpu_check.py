@@ -76,7 +76,7 @@ def time_operator(mod, case, iters=10, warmup=3):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--cases", default="c0,c0_bg,c0_deg0,c0_precomp,ragged")
+    ap.add_argument("--cases", default="tiny,c0,c0_bg,c0_deg0,c0_precomp,ragged,scalemod")
     ap.add_argument("--time", default="c1,c2")
     ap.add_argument("--out", default=str(ROOT / "gpurun_out" / "gpu_check.json"))
     args = ap.parse_args()
@@ -89,20 +89,8 @@ def main():
     results = {"device": torch.cuda.get_device_name(0), "parity": {}, "timing": {}}
 
     def build(name):
-        if name == "c0":
-            return Hh.room_case("c0")
-        if name == "c0_bg":
-            return Hh.room_case("c0_bg", bg=np.array([0.3, 0.6, 0.9], np.float32), seed=5)
-        if name == "c0_deg0":
-            return Hh.room_case("c0_deg0", sh_degree=0, seed=6)
-        if name == "ragged":
-            return Hh.room_case("ragged", P=5000, W=250, H=131, seed=7, sh_degree=2)
-        if name == "c0_precomp":
-            c = Hh.room_case("c0_precomp", seed=8)
-            st = Hh.run_oracle(o32, c, backward=False)["_state"]
-            c.colors_precomp = st["rgb"].copy()
-            c.transMat_precomp = st["transMats"].copy()
-            return c
+        if name in Hh.NAMED_CASES:
+            return Hh.named_case(name, o32)
         cfg = S.CONFIGS[name]
         return Hh.room_case(name, P=cfg["P"], W=cfg["W"], H=cfg["H"], seed=cfg["seed"], cams=cfg["cams"])
 
