@@ -147,7 +147,33 @@ class Workload:
         rng = np.random.default_rng(123 + rank)
         self.gt_host = [torch.from_numpy(rng.integers(0, 256, size=(3, self.H, self.W), dtype=np.uint8)).pin_memory()
                         for _ in range(8)]
-        self.gt_dev = torch.empty((3, self.H, self.W), dtype=torch.uint8, device=device)
+        # double-buffered device copies filled by a side stream: the next view's image travels over
+        # PCIe while the current view is rendered (what a data loader with pinned memory does)
+        self.gt_dev = [torch.empty((3, self.H, self.W), dtype=torch.uint8, device=device) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.copy_done = [torch.cuda.Event(), torch.cuda.Event()]
+        self.slot_free = [torch.cuda.Event(), torch.cuda.Event()]
+        self._slot = 0
+
+    def prefetch_image(self, index: int):
+        """Start the host->device copy of photograph `index` into the next free slot (side stream)."""
+        import torch
+        slot = self._slot
+        self._slot ^= 1
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.slot_free[slot])   # the loss that last read this slot has been issued
+            self.gt_dev[slot].copy_(self.gt_host[index % len(self.gt_host)], non_blocking=True)
+            self.copy_done[slot].record(self.copy_stream)
+        return slot
+
+    def image(self, slot: int):
+        import torch
+        torch.cuda.current_stream(self.device).wait_event(self.copy_done[slot])
+        return self.gt_dev[slot]
+
+    def release_image(self, slot: int):
+        import torch
+        self.slot_free[slot].record(torch.cuda.current_stream(self.device))
 
     def view_ids(self, step: int):
         base = (step * self.world + self.rank) * self.vps
@@ -175,13 +201,17 @@ def run_steps(wl: Workload, mod, sync, steps: int, first_step: int, e2e: bool):
     """`steps` optimisation-step-shaped passes; returns the last loss value (e2e) or None."""
     import torch
     last = None
+    slot = wl.prefetch_image(first_step) if e2e else None
     for s in range(first_step, first_step + steps):
         loss_acc = None
         for k, vid in enumerate(wl.view_ids(s)):
+            if e2e:
+                nxt = wl.prefetch_image(s + k + 1)           # next view's photograph: PCIe copy overlaps this view
             color, radii, allmap, means2D = wl.rasterize(mod, vid)
             if e2e:
-                wl.gt_dev.copy_(wl.gt_host[(s + k) % len(wl.gt_host)], non_blocking=True)
-                gt = wl.gt_dev.to(torch.float32) * (1.0 / 255.0)
+                gt = wl.image(slot).to(torch.float32) * (1.0 / 255.0)
+                wl.release_image(slot)
+                slot = nxt
                 loss = (color - gt).abs().mean() + 0.05 * allmap[6].mean() + 0.01 * (allmap[0] + allmap[5]).mean() \
                     + 0.01 * allmap[1:5].mean()
                 loss.backward()
