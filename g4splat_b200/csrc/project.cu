@@ -24,39 +24,42 @@ __device__ const float SH_C3[] = {-0.5900435899266435f, 2.890611442640554f, -0.4
                                   0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
                                   -0.5900435899266435f};
 
-// Degree-D real SH -> RGB for one Gaussian, + 0.5, clamp at 0 (CR/forward.cu:20-71).
+// Degree-D real SH -> RGB for one Gaussian, + 0.5, clamp at 0 (CR/forward.cu:20-71).  Rounding pinned
+// to the reference's SASS: every term is accumulated with one fma(coef, sh, r); the coefficients are
+// rounded products, with xx*3 - yy, zz*4 - xx, 2zz - 3xx - 3yy and xx - 3yy fused as fma(.., +-3|4, ..).
 __device__ __forceinline__ f3 sh_to_rgb(int deg, const float* __restrict__ sh /* [M][3] */, f3 dir,
                                         uint8_t& clamp_mask) {
-    auto c = [&](int k) { return mk3(sh[3 * k], sh[3 * k + 1], sh[3 * k + 2]); };
-    f3 r = scale3(SH_C0, c(0));
+    f3 r = mk3(__fmul_rn(SH_C0, sh[0]), __fmul_rn(SH_C0, sh[1]), __fmul_rn(SH_C0, sh[2]));
+    auto acc = [&](float k, int i) {
+        r.x = __fmaf_rn(k, sh[3 * i], r.x); r.y = __fmaf_rn(k, sh[3 * i + 1], r.y); r.z = __fmaf_rn(k, sh[3 * i + 2], r.z);
+    };
     if (deg > 0) {
         const float x = dir.x, y = dir.y, z = dir.z;
-        f3 a = c(1), b = c(2), d = c(3);
-        const float c1y = SH_C1 * y, c1z = SH_C1 * z, c1x = SH_C1 * x;
-        r = mk3(r.x - c1y * a.x + c1z * b.x - c1x * d.x, r.y - c1y * a.y + c1z * b.y - c1x * d.y,
-                r.z - c1y * a.z + c1z * b.z - c1x * d.z);
+        acc(-__fmul_rn(SH_C1, y), 1);
+        acc(__fmul_rn(SH_C1, z), 2);
+        acc(-__fmul_rn(SH_C1, x), 3);
         if (deg > 1) {
-            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-            const float k4 = SH_C2[0] * xy, k5 = SH_C2[1] * yz, k6 = SH_C2[2] * (2.0f * zz - xx - yy),
-                        k7 = SH_C2[3] * xz, k8 = SH_C2[4] * (xx - yy);
-            f3 s4 = c(4), s5 = c(5), s6 = c(6), s7 = c(7), s8 = c(8);
-            r = mk3(r.x + k4 * s4.x + k5 * s5.x + k6 * s6.x + k7 * s7.x + k8 * s8.x,
-                    r.y + k4 * s4.y + k5 * s5.y + k6 * s6.y + k7 * s7.y + k8 * s8.y,
-                    r.z + k4 * s4.z + k5 * s5.z + k6 * s6.z + k7 * s7.z + k8 * s8.z);
+            const float xx = __fmul_rn(x, x), yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+            const float xy = __fmul_rn(x, y), yz = __fmul_rn(y, z), xz = __fmul_rn(x, z);
+            const float zz2 = __fadd_rn(zz, zz), xx_yy = __fsub_rn(xx, yy);
+            acc(__fmul_rn(SH_C2[0], xy), 4);
+            acc(__fmul_rn(SH_C2[1], yz), 5);
+            acc(__fmul_rn(SH_C2[2], __fsub_rn(__fsub_rn(zz2, xx), yy)), 6);
+            acc(__fmul_rn(SH_C2[3], xz), 7);
+            acc(__fmul_rn(SH_C2[4], xx_yy), 8);
             if (deg > 2) {
-                const float k9 = SH_C3[0] * y * (3.0f * xx - yy), k10 = SH_C3[1] * xy * z,
-                            k11 = SH_C3[2] * y * (4.0f * zz - xx - yy),
-                            k12 = SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy),
-                            k13 = SH_C3[4] * x * (4.0f * zz - xx - yy), k14 = SH_C3[5] * z * (xx - yy),
-                            k15 = SH_C3[6] * x * (xx - 3.0f * yy);
-                f3 s9 = c(9), s10 = c(10), s11 = c(11), s12 = c(12), s13 = c(13), s14 = c(14), s15 = c(15);
-                r = mk3(r.x + k9 * s9.x + k10 * s10.x + k11 * s11.x + k12 * s12.x + k13 * s13.x + k14 * s14.x + k15 * s15.x,
-                        r.y + k9 * s9.y + k10 * s10.y + k11 * s11.y + k12 * s12.y + k13 * s13.y + k14 * s14.y + k15 * s15.y,
-                        r.z + k9 * s9.z + k10 * s10.z + k11 * s11.z + k12 * s12.z + k13 * s13.z + k14 * s14.z + k15 * s15.z);
+                const float zz4_xx_yy = __fsub_rn(__fmaf_rn(zz, 4.0f, -xx), yy);
+                acc(__fmul_rn(__fmul_rn(SH_C3[0], y), __fmaf_rn(xx, 3.0f, -yy)), 9);
+                acc(__fmul_rn(__fmul_rn(SH_C3[1], xy), z), 10);
+                acc(__fmul_rn(__fmul_rn(SH_C3[2], y), zz4_xx_yy), 11);
+                acc(__fmul_rn(__fmul_rn(SH_C3[3], z), __fmaf_rn(yy, -3.0f, __fmaf_rn(xx, -3.0f, zz2))), 12);
+                acc(__fmul_rn(__fmul_rn(SH_C3[4], x), zz4_xx_yy), 13);
+                acc(__fmul_rn(__fmul_rn(SH_C3[5], z), xx_yy), 14);
+                acc(__fmul_rn(__fmul_rn(SH_C3[6], x), __fmaf_rn(yy, -3.0f, xx)), 15);
             }
         }
     }
-    r = mk3(r.x + 0.5f, r.y + 0.5f, r.z + 0.5f);
+    r = mk3(__fadd_rn(r.x, 0.5f), __fadd_rn(r.y, 0.5f), __fadd_rn(r.z, 0.5f));
     clamp_mask = (uint8_t)((r.x < 0 ? 1 : 0) | (r.y < 0 ? 2 : 0) | (r.z < 0 ? 4 : 0));
     return mk3(fmaxf(r.x, 0.0f), fmaxf(r.y, 0.0f), fmaxf(r.z, 0.0f));
 }
@@ -190,8 +193,8 @@ __device__ __forceinline__ bool project_one(const ProjectArgs& a, int idx, ProjO
     o.clamp_mask = 0;
     if (a.colors_precomp == nullptr) {
         f3 dir = sub3(p, mk3(a.campos[0], a.campos[1], a.campos[2]));
-        const float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
-        dir = mk3(dir.x / len, dir.y / len, dir.z / len);
+        const float len = __fsqrt_rn(dot3_rn(dir.x, dir.x, dir.y, dir.y, dir.z, dir.z));
+        dir = mk3(__fdiv_rn(dir.x, len), __fdiv_rn(dir.y, len), __fdiv_rn(dir.z, len));
         o.rgb = sh_to_rgb(a.D, a.shs + (size_t)idx * a.M * 3, dir, o.clamp_mask);
     } else {
         o.rgb = mk3(a.colors_precomp[3 * idx], a.colors_precomp[3 * idx + 1], a.colors_precomp[3 * idx + 2]);
