@@ -50,6 +50,19 @@ def test_install_registers_the_reference_import_name():
     del sys.modules["diff_surfel_rasterization"]
 
 
+def test_root_level_import_name_shim():
+    """`import diff_surfel_rasterization` with the repo root on sys.path is the B200 operator."""
+    import importlib
+    import sys
+    sys.modules.pop("diff_surfel_rasterization", None)
+    mod = importlib.import_module("diff_surfel_rasterization")
+    import g4splat_b200.diff_surfel_rasterization as op
+    assert mod.GaussianRasterizer is op.GaussianRasterizer
+    assert mod.GaussianRasterizationSettings is op.GaussianRasterizationSettings
+    assert mod.rasterize_gaussians is op.rasterize_gaussians
+    sys.modules.pop("diff_surfel_rasterization", None)
+
+
 def test_capacity_policy():
     from g4splat_b200.diff_surfel_rasterization import _CapacityPolicy
     p = _CapacityPolicy()

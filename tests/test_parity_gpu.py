@@ -405,3 +405,31 @@ def test_non_default_stream_and_interleaved_views(b200, oracle32):
     want = singles[0]["dL_dmeans3D"] + singles[1]["dL_dmeans3D"]
     r = Hh.parity(p["means3D"].grad.cpu().numpy(), want, 1e-4)
     assert r["bad_frac"] == 0, r
+
+
+def test_size_independent_properties_at_full_size(b200):
+    """BASELINE config 2 at full size without any reference: (1) the forward is deterministic,
+    (2) the backward is linear in the upstream gradients (grads(2 g) == 2 grads(g) up to the
+    atomic-order noise), (3) a fully transparent scene renders the background and zero gradients."""
+    import torch
+    from g4splat_b200 import synthetic as S
+    c = S.CONFIGS["c2"]
+    case = Hh.room_case("c2", P=c["P"], W=c["W"], H=c["H"], seed=c["seed"], cams=c["cams"])
+    a = Hh.run_operator(b200, case)
+    b = Hh.run_operator(b200, case)
+    for k in ("color", "allmap", "radii"):
+        assert np.array_equal(a[k], b[k]), k
+    up = case.upstream
+    case.upstream = lambda: tuple(2.0 * g for g in up())
+    d = Hh.run_operator(b200, case)
+    for k in Hh.GRAD_KEYS:
+        r = Hh.parity(d[k], 2.0 * a[k], 1e-4)
+        assert r["bad_frac"] <= 1e-6, (k, r)
+    case.upstream = up
+    case.scene["opacities"] = case.scene["opacities"] * 0 + 1e-3   # alpha < 1/255 everywhere
+    case.bg = np.array([0.25, 0.5, 0.75], np.float32)
+    e = Hh.run_operator(b200, case)
+    assert np.allclose(e["color"].reshape(3, -1).T, case.bg) and not e["allmap"].any()
+    assert (e["radii"] > 0).any()
+    for k in Hh.GRAD_KEYS:
+        assert not e[k].any(), k

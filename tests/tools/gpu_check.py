@@ -1,7 +1,7 @@
 """Run on the GPU box: parity tables (B200 operator vs CPU oracle vs reference extension) and
 per-stage timings; writes gpurun_out/gpu_check.json.  Not part of the product path.
 
-  python tools/gpu_check.py [--cases c0,c0_bg,...] [--time c1,c2]
+  python tests/tools/gpu_check.py [--cases c0,c0_bg,...] [--time c1,c2]
 """
 from __future__ import annotations
 
@@ -14,7 +14,7 @@ from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 

@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU-box session: tests, golden vectors, bench (both arms), ncu launch list + full capture.
-# Usage (from the repo root, under gpurun):  bash tools/gpu_round.sh [tag] [parts...]
+# Usage (from the repo root, under gpurun):  bash tests/tools/gpu_round.sh [tag] [parts...]
 #   parts: tests golden bench ncu  (default: all)
 TAG=${1:-r01}; shift
 PARTS=${@:-tests golden bench ncu}

@@ -1,7 +1,7 @@
 """Summarise ncu captures into profiles/ (tracked): per-kernel time shares from a launch list
 (`--metrics gpu__time_duration.sum`) and key counters from a `--set full` report.
 
-  python tools/ncu_summary.py <tag>      # reads gpurun_out/<tag>_launches.csv, gpurun_out/<tag>_prof.ncu-rep
+  python tests/tools/ncu_summary.py <tag>      # reads gpurun_out/<tag>_launches.csv, gpurun_out/<tag>_prof.ncu-rep
 """
 import collections
 import csv
@@ -9,7 +9,7 @@ import subprocess
 import sys
 from pathlib import Path
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
