@@ -364,6 +364,19 @@ def main():
     h2d = args.views * (3 * N)          # one uint8 image per view
     d2h = 4                             # the scalar loss
 
+    pair_stats = None
+    if lib is not None and rank == 0:
+        import g4splat_b200.diff_surfel_rasterization as op_mod
+        acc = {}
+        vids = list(wl.view_ids(warmup))
+        for vid in vids:                 # untimed: work counters of the views of one step
+            color = wl.rasterize(mod, vid)[0]
+            for k, v in op_mod.debug_pair_stats(color).items():
+                acc[k] = max(acc.get(k, 0), v) if k == "longest_tile_list" else acc.get(k, 0) + v
+            del color
+        pair_stats = {k: (v if k == "longest_tile_list" else v / len(vids)) for k, v in acc.items()}
+        sync.zero()
+
     if rank != 0:
         if dist_on:
             dist.destroy_process_group()
@@ -411,6 +424,21 @@ def main():
         line["path"] = {"alg_bytes_per_view": pb, "kernel_ms_per_view": per_view_ms, "visible": V, "num_rendered": R,
                         "hbm_frac_of_kernel_time": (pb / (per_view_ms * 1e-3) / 1e9 / peak) if per_view_ms > 0 else None,
                         "hbm_frac_of_step_time": pb * args.views / (ms / args.steps * 1e-3) / 1e9 / peak}
+        if pair_stats is not None and stage_ms.get("blend_fwd", 0) > 0 and stage_ms.get("blend_bwd", 0) > 0:
+            # secondary roofline: algorithmic ~60 flop per blended pair forward, ~200 backward,
+            # against the fp32 SIMT peak 148 SMs x 128 lanes x 2 flop x SM clock under load
+            mhz = (clk or {}).get("sm_mhz") or 1965.0
+            fp32_peak = 148 * 128 * 2 * mhz * 1e6
+            pb_, pe_ = pair_stats["pairs_blended"], pair_stats["pair_evals_bwd"]
+            fwd_s, bwd_s = stage_ms["blend_fwd"] * 1e-3, stage_ms["blend_bwd"] * 1e-3
+            line["compute_roofline"] = {
+                "per_view": pair_stats, "fp32_peak_TFLOPs": fp32_peak / 1e12,
+                "blend_fwd": {"Gpairs_per_s": pb_ / fwd_s / 1e9, "alg_flop_per_pair": 60,
+                              "frac_of_fp32_peak": 60 * pb_ / fwd_s / fp32_peak},
+                "blend_bwd": {"Gpairs_per_s": pb_ / bwd_s / 1e9, "alg_flop_per_pair": 200,
+                              "frac_of_fp32_peak": 200 * pb_ / bwd_s / fp32_peak,
+                              "lane_utilisation": pb_ / pe_ if pe_ else None},
+                "lane_slots_skipped_by_culling": 1.0 - pe_ / pair_stats["pair_slots"] if pair_stats["pair_slots"] else None}
         if not args.no_cpu_baseline and world == 1:
             v, cores, dt = cpu_oracle_step()
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

@@ -32,6 +32,7 @@ SIGNATURES = {
     "g4s_profile_read": (_i, [_vp, _vp, _i]),
     "g4s_debug_decode_geom": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4s_debug_decode_lists": (_i, [_i, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "g4s_debug_pair_stats": (_i, [_i, _i, _vp, _i, _vp, _vp, _i64, _vp, _vp]),
 }
 
 _lib = None

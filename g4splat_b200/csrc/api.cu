@@ -303,6 +303,46 @@ __global__ void decode_ranges_kernel(int T, const uint32_t* tile_offset, uint32_
     ranges[2 * i] = tile_offset[i];
     ranges[2 * i + 1] = tile_offset[i + 1];
 }
+// One CTA per tile, one warp per 8x4 region, the same walk as the backward: positions below the warp's last
+// contributor whose box meets the region carry a valid forward mask.
+__global__ void pair_stats_kernel(int W, int H, int grid_x, const uint32_t* tile_offset, const uint32_t* list,
+                                  const uint32_t* masks, const float4* rec, const uint32_t* n_contrib,
+                                  unsigned long long* out) {
+    const int tile = blockIdx.x, ty = tile / grid_x, tx = tile - ty * grid_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bx = tx * TILE + (warp & 1) * REGION_W, by = ty * TILE + (warp >> 1) * REGION_H;
+    const int px = bx + (lane & 7), py = by + (lane >> 3);
+    const float rx0 = (float)bx, ry0 = (float)by;
+    const float rx1 = (float)min(bx + REGION_W - 1, W - 1), ry1 = (float)min(by + REGION_H - 1, H - 1);
+    const uint32_t off = tile_offset[tile];
+    const int n = (int)(tile_offset[tile + 1] - off);
+    int last = (px < W && py < H) ? (int)n_contrib[(size_t)W * py + px] : 0;
+    unsigned long long walked = last, blended = 0, issued = 0;
+    int warp_last = last;
+    for (int o = 16; o; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(~0u, warp_last, o));
+    for (int pos = lane; pos < min(n, warp_last); pos += 32) {
+        const float4 bb = rec[(size_t)list[off + pos] * REC_F4];
+        if (bb.x <= rx1 && bb.z >= rx0 && bb.y <= ry1 && bb.w >= ry0) {
+            const uint32_t m = masks[(size_t)(off + pos) * 8 + warp];
+            blended += __popc(m);
+            issued += m ? 32 : 0;
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        blended += __shfl_xor_sync(~0u, blended, o);
+        walked += __shfl_xor_sync(~0u, walked, o);
+        issued += __shfl_xor_sync(~0u, issued, o);
+    }
+    if (lane == 0) {
+        atomicAdd(out + 0, blended);
+        atomicAdd(out + 1, walked);
+        atomicAdd(out + 4, issued);
+        if (warp == 0) {
+            atomicAdd(out + 2, (unsigned long long)n * (TILE * TILE));
+            atomicMax(out + 3, (unsigned long long)n);
+        }
+    }
+}
 }  // namespace g4s
 
 int g4s_debug_decode_geom(int P, const void* geom_buffer, float* transMat, float* means2D, float* normal_opacity,
@@ -331,6 +371,23 @@ int g4s_debug_decode_lists(int W, int H, const void* img_buffer, const void* bin
     if (point_list && binning_buffer && capacity > 0 &&
         (rc = check_cuda(cudaMemcpyAsync(point_list, bin.list, (size_t)capacity * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s), "copy list"))) return rc;
     return stage_check(false, s, "decode_lists");
+}
+
+int g4s_debug_pair_stats(int W, int H, const void* geom_buffer, int P, const void* img_buffer, const void* binning_buffer,
+                         int64_t capacity, uint64_t* stats, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    GeomView geom;
+    ImageView img;
+    BinView bin;
+    geom_layout(P, (char*)geom_buffer, &geom);
+    image_layout(W, H, (char*)img_buffer, &img);
+    bin_layout(capacity, (char*)binning_buffer, &bin);
+    const int gx = (W + TILE - 1) / TILE, T = gx * ((H + TILE - 1) / TILE);
+    int rc;
+    if ((rc = check_cuda(cudaMemsetAsync(stats, 0, 8 * sizeof(uint64_t), s), "clear pair stats"))) return rc;
+    pair_stats_kernel<<<T, TILE_PIX, 0, s>>>(W, H, gx, img.tile_offset, bin.list, bin.masks, geom.rec, img.n_contrib,
+                                             (unsigned long long*)stats);
+    return stage_check(false, s, "pair_stats");
 }
 
 }  // extern "C"

@@ -300,6 +300,30 @@ class _RasterizeGaussians(torch.autograd.Function):
                 dL_dtransMat, None)
 
 
+def debug_pair_stats(rendered: torch.Tensor) -> dict:
+    """Work counters of the view that produced `rendered` (the colour or allmap output of a call that
+    required grad): pairs blended, sum over pixels of the last contributor's position in the culled lists,
+    pair slots (256 per list entry), longest tile list, pair evaluations the B200 backward issues (g4s_debug_pair_stats).  Benchmark / test introspection;
+    no reference counterpart (SURVEY.md 8d asks for pairs/s against the fp32 peak)."""
+    ctx = rendered.grad_fn
+    if ctx is None or not hasattr(ctx, "raster_settings"):
+        raise RuntimeError("debug_pair_stats needs an output of the rasterizer that is attached to the graph")
+    saved = ctx.saved_tensors
+    geom, binning, img = saved[-3:]
+    rs = ctx.raster_settings
+    P = int(saved[1].shape[0])
+    keys = ("pairs_blended", "pairs_walked", "pair_slots", "longest_tile_list", "pair_evals_bwd")
+    if P == 0:
+        return dict.fromkeys(keys, 0)
+    lib = _lib.load()
+    stats = torch.zeros(8, dtype=torch.int64, device=geom.device)
+    with torch.cuda.device(geom.device):
+        _lib.check(lib.g4s_debug_pair_stats(int(rs.image_width), int(rs.image_height), geom.data_ptr(), P, img.data_ptr(),
+                                            binning.data_ptr(), int(ctx.capacity), stats.data_ptr(),
+                                            torch.cuda.current_stream(geom.device).cuda_stream))
+    return dict(zip(keys, (int(v) for v in stats[:5].tolist())))
+
+
 class GaussianRasterizationSettings(NamedTuple):
     image_height: int
     image_width: int

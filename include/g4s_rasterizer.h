@@ -148,6 +148,14 @@ int g4s_debug_decode_geom(int P, const void* geom_buffer, float* transMat, float
 int g4s_debug_decode_lists(int W, int H, const void* img_buffer, const void* binning_buffer,
                            int64_t capacity, uint32_t* ranges, float* final_T, uint32_t* n_contrib,
                            uint32_t* point_list, void* stream);
+/* Work counters of one rendered view (secondary roofline) from its three scratch
+ * buffers (valid after g4s_forward_render with num_rendered <= capacity), DEVICE uint64 stats[8]:
+ *   [0] (pixel, surfel) pairs the forward blended  [1] sum over pixels of the last contributor's
+ *   position in this library's (culled) tile lists  [2] pair slots = 256 * num_rendered
+ *   [3] longest tile list  [4] pair evaluations this library's backward issues (32 lanes per
+ *   (instance, 8x4 region) whose forward mask is non-zero)  [5..7] zero */
+int g4s_debug_pair_stats(int W, int H, const void* geom_buffer, int P, const void* img_buffer,
+                         const void* binning_buffer, int64_t capacity, uint64_t* stats, void* stream);
 /* number of kernel launches issued by this library since process start (bench: gpu_launches) */
 int64_t g4s_launch_count(void);
 /* Per-stage CUDA-event timers on the launch stream (process-global, for bench.py / profiling;

@@ -114,11 +114,14 @@ class Oracle:
         st["out_others"] = np.zeros((7, H, W), rt)
         st["final_T"] = np.zeros((3, H, W), rt)
         st["n_contrib"] = np.zeros((2, H, W), np.uint32)
+        st["pairs_per_pixel"] = np.zeros((H, W), np.uint32)
         if P:
+            self.lib.orc_set_pair_counter(_ptr(st["pairs_per_pixel"]))
             self.lib.orc_blend_forward(
                 C.c_int(W), C.c_int(H), _ptr(st["ranges"]), _ptr(st["point_list"]), _ptr(st["means2D"]),
                 _ptr(st["features"]), _ptr(st["transMat_used"]), _ptr(st["normal_opacity"]), _ptr(bg),
                 _ptr(st["out_color"]), _ptr(st["out_others"]), _ptr(st["final_T"]), _ptr(st["n_contrib"]))
+            self.lib.orc_set_pair_counter(None)
         # keep inputs for backward
         st.update(_means3D=means3D, _shs=shs, _colors_precomp=colors_precomp, _scales=scales,
                   _rotations=rotations, _transMat_precomp=transMat_precomp, _view=view, _proj=proj,

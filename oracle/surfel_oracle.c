@@ -348,6 +348,11 @@ int orc_bin(int P, int W, int H, const real* means2D, const real* depths, const 
 /* CR/forward.cu:258-443  renderCUDA (forward).  One pixel at a time; the block-level
  * "all 256 threads done" early exit (:327-329) only skips work whose results are discarded.
  * features = colors_precomp or the rgb from orc_project ([P,3]).                          */
+/* test instrumentation (no reference counterpart): when set, pixel p's number of blended
+ * (pixel, surfel) pairs is stored at pairs_per_pixel[p] by the next orc_blend_forward calls. */
+static uint32_t* g_pairs_per_pixel = 0;
+void orc_set_pair_counter(uint32_t* pairs_per_pixel) { g_pairs_per_pixel = pairs_per_pixel; }
+
 void orc_blend_forward(int W, int H, const uint32_t* ranges, const uint32_t* point_list, const real* means2D,
                        const real* features, const real* transMats, const real* normal_opacity, const real* bg,
                        real* out_color, real* out_others, real* final_T, uint32_t* n_contrib) {
@@ -364,7 +369,7 @@ void orc_blend_forward(int W, int H, const uint32_t* ranges, const uint32_t* poi
                 const size_t pix_id = (size_t)W * pyi + pxi;
                 const real pxf = (real)pxi, pyf = (real)pyi;
                 real T = 1;
-                uint32_t contributor = 0, last_contributor = 0;
+                uint32_t contributor = 0, last_contributor = 0, blended = 0;
                 real C[3] = {0, 0, 0}, N[3] = {0, 0, 0};
                 real Dd = 0, M1 = 0, M2 = 0, distortion = 0, median_depth = 0;
                 real median_contributor = -1;
@@ -405,7 +410,9 @@ void orc_blend_forward(int W, int H, const uint32_t* ranges, const uint32_t* poi
                     for (int ch = 0; ch < 3; ch++) C[ch] += features[3 * (size_t)g + ch] * w;
                     T = test_T;
                     last_contributor = contributor;
+                    blended++;
                 }
+                if (g_pairs_per_pixel) g_pairs_per_pixel[pix_id] = blended;
                 final_T[pix_id] = T;
                 n_contrib[pix_id] = last_contributor;
                 for (int ch = 0; ch < 3; ch++) out_color[ch * HW + pix_id] = C[ch] + T * bg[ch];

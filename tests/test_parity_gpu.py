@@ -433,3 +433,26 @@ def test_size_independent_properties_at_full_size(b200):
     assert (e["radii"] > 0).any()
     for k in Hh.GRAD_KEYS:
         assert not e[k].any(), k
+
+
+@pytest.mark.parametrize("name", ["tiny", "c0"])
+def test_pair_stats_match_oracle(b200, oracle32, name):
+    """g4s_debug_pair_stats (the counters bench.py's secondary roofline uses) against the oracle's
+    per-pixel count of blended pairs."""
+    import torch
+    import g4splat_b200.diff_surfel_rasterization as op
+    case = Hh.named_case(name)
+    ref = Hh.run_oracle(oracle32, case, backward=False)["_state"]
+    sc = case.scene
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+    means3D = t(sc["means3D"]).requires_grad_(True)
+    rast = op.GaussianRasterizer(raster_settings=Hh.make_settings(op, case, "cuda", False))
+    color, radii, allmap = rast(means3D=means3D, means2D=torch.zeros_like(means3D), opacities=t(sc["opacities"]),
+                                shs=t(sc["shs"]), scales=t(sc["scales"]), rotations=t(sc["rotations"]))
+    st = op.debug_pair_stats(color)
+    want = int(ref["pairs_per_pixel"].sum())
+    assert want > 0 and abs(st["pairs_blended"] - want) <= max(2, 1e-4 * want), (st, want)
+    assert st["pair_slots"] == 256 * op.last_counts["num_rendered"]
+    assert st["longest_tile_list"] == op.last_counts["max_tile_list"]
+    assert st["pairs_blended"] <= st["pairs_walked"] <= int(ref["n_contrib"][0].astype(np.int64).sum())
+    assert st["pairs_blended"] <= st["pair_evals_bwd"] <= st["pair_slots"]

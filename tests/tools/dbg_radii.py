@@ -1,11 +1,11 @@
 import sys, json
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+sys.path.insert(0,'.'); sys.path.insert(0,'./tests')
 import numpy as np, torch, helpers as Hh
 import g4splat_b200.diff_surfel_rasterization as op
 from oracle.oracle import Oracle
 from oracle import build_ref
 o=Oracle('f32'); o.set_threads(1)
-z=np.load('/root/repo/tests/golden/c0_bg.npz')
+z=np.load('./tests/golden/c0_bg.npz')
 case=Hh.case_from_meta(json.loads(str(z['meta'])), o)
 got=Hh.run_operator(op, case, backward=False)
 ref=Hh.run_operator(build_ref.import_reference(), case, backward=False)
