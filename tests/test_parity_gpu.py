@@ -456,3 +456,26 @@ def test_pair_stats_match_oracle(b200, oracle32, name):
     assert st["longest_tile_list"] == op.last_counts["max_tile_list"]
     assert st["pairs_blended"] <= st["pairs_walked"] <= int(ref["n_contrib"][0].astype(np.int64).sum())
     assert st["pairs_blended"] <= st["pair_evals_bwd"] <= st["pair_slots"]
+
+
+def test_nonfinite_upstream_grads_at_empty_pixels_are_ignored(b200):
+    """render() divides depth by alpha (gaussian_renderer/__init__.py:133-134): where nothing was
+    blended its autograd hands the operator NaN upstream gradients.  The reference never reads them
+    (its loop is bounded by the pixel's last contributor, CR/backward.cu:291); neither may we."""
+    case = _dense_case(40, 160, 96, 7, 0.05, 0.8)
+    base = Hh.run_operator(b200, case)
+    empty = base["allmap"][1] == 0
+    assert 0.2 < empty.mean() < 0.98, empty.mean()
+    up = case.upstream
+    def poisoned():
+        gc, go = up()
+        gc, go = gc.copy(), go.copy()
+        gc[:, empty] = np.nan
+        go[:, empty] = np.nan
+        go[0][empty] = np.inf
+        return gc, go
+    case.upstream = poisoned
+    got = Hh.run_operator(b200, case)
+    for k in Hh.GRAD_KEYS:
+        assert np.isfinite(got[k]).all(), k
+    Hh.assert_parity(got, base, Hh.GRAD_KEYS, rtol=1e-5, max_bad_frac=GRAD_BUDGET, what="poisoned upstream")
