@@ -8,7 +8,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libg4s_rasterizer.so"
 
-_vp, _i, _f, _i64, _sz = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
+_vp, _i, _f, _i64, _sz, _d = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t, C.c_double
 
 # name -> (restype, argtypes); mirrors include/g4s_rasterizer.h one to one
 SIGNATURES = {
@@ -30,6 +30,8 @@ SIGNATURES = {
     "g4s_profile_num_stages": (_i, []),
     "g4s_profile_stage_name": (C.c_char_p, [_i]),
     "g4s_profile_read": (_i, [_vp, _vp, _i]),
+    "g4s_surface_forward": (_i, [_i, _i, _vp, _vp, _vp, _d] + [_vp] * 8 + [_vp]),
+    "g4s_surface_backward": (_i, [_i, _i, _vp, _vp, _vp, _d] + [_vp] * 8 + [_vp, _vp]),
     "g4s_debug_decode_geom": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4s_debug_decode_lists": (_i, [_i, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "g4s_debug_pair_stats": (_i, [_i, _i, _vp, _i, _vp, _vp, _i64, _vp, _vp]),

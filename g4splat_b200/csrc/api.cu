@@ -276,6 +276,35 @@ int g4s_densify_stats(int P, const float* dL_dmeans2D, const int* radii, float* 
     return stage_check(false, (cudaStream_t)stream, "densify_stats");
 }
 
+int g4s_surface_forward(int W, int H, const float* allmap, const float* viewmatrix, const float* projmatrix,
+                        double depth_ratio, float* rend_alpha, float* rend_normal, float* rend_normal_cam, float* rend_dist,
+                        float* surf_depth, float* surf_normal, float* surf_normal_cam, float* rend_depth, void* stream) {
+    if (W < 0 || H < 0) return fail(G4S_EINVAL, "surface_forward: negative image size");
+    if (W == 0 || H == 0) return G4S_OK;
+    if (!allmap || !viewmatrix || !projmatrix || !rend_alpha || !rend_normal || !rend_normal_cam || !rend_dist ||
+        !surf_depth || !surf_normal || !surf_normal_cam || !rend_depth)
+        return fail(G4S_EINVAL, "surface_forward: null pointer");
+    SurfaceFwdArgs a{W, H, (float)(1.0 - depth_ratio), (float)depth_ratio, allmap, viewmatrix, projmatrix,
+                     rend_alpha, rend_normal, rend_normal_cam, rend_dist, surf_depth, surf_normal, surf_normal_cam, rend_depth};
+    launch_surface_fwd(a, (cudaStream_t)stream);
+    return stage_check(false, (cudaStream_t)stream, "surface_fwd");
+}
+
+int g4s_surface_backward(int W, int H, const float* allmap, const float* viewmatrix, const float* projmatrix,
+                         double depth_ratio, const float* dL_drend_alpha, const float* dL_drend_normal,
+                         const float* dL_drend_normal_cam, const float* dL_drend_dist, const float* dL_dsurf_depth,
+                         const float* dL_dsurf_normal, const float* dL_dsurf_normal_cam, const float* dL_drend_depth,
+                         float* dL_dallmap, void* stream) {
+    if (W < 0 || H < 0) return fail(G4S_EINVAL, "surface_backward: negative image size");
+    if (W == 0 || H == 0) return G4S_OK;
+    if (!allmap || !viewmatrix || !projmatrix || !dL_dallmap) return fail(G4S_EINVAL, "surface_backward: null pointer");
+    SurfaceBwdArgs a{W, H, (float)(1.0 - depth_ratio), (float)depth_ratio, allmap, viewmatrix, projmatrix,
+                     dL_drend_alpha, dL_drend_normal, dL_drend_normal_cam, dL_drend_dist, dL_dsurf_depth,
+                     dL_dsurf_normal, dL_dsurf_normal_cam, dL_drend_depth, dL_dallmap};
+    launch_surface_bwd(a, (cudaStream_t)stream);
+    return stage_check(false, (cudaStream_t)stream, "surface_bwd");
+}
+
 // ---- introspection ---------------------------------------------------------------------------
 namespace g4s {
 __global__ void decode_geom_kernel(int P, GeomView geom, float* transMat, float* means2D, float* normal_opacity,

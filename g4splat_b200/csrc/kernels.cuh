@@ -101,4 +101,27 @@ void launch_densify_stats(int P, const float* dL_dmeans2D, const int* radii, flo
                           int* max_radii, cudaStream_t s);
 void launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s);
 
+// ---- render() post-processing (surface.cu) ----------------------------------------------------
+struct SurfaceFwdArgs {
+    int W, H;
+    float r0, r1;            // (float)(1 - depth_ratio), (float)depth_ratio
+    const float* allmap;     // [7][N]
+    const float* view; const float* proj;
+    float* rend_alpha; float* rend_normal; float* rend_normal_cam; float* rend_dist;
+    float* surf_depth; float* surf_normal; float* surf_normal_cam; float* rend_depth;
+};
+void launch_surface_fwd(const SurfaceFwdArgs& a, cudaStream_t s);
+
+struct SurfaceBwdArgs {
+    int W, H;
+    float r0, r1;
+    const float* allmap;
+    const float* view; const float* proj;
+    // upstream gradients, any may be null (= zeros)
+    const float* g_rend_alpha; const float* g_rend_normal; const float* g_rend_normal_cam; const float* g_rend_dist;
+    const float* g_surf_depth; const float* g_surf_normal; const float* g_surf_normal_cam; const float* g_rend_depth;
+    float* g_allmap;         // [7][N], every element written
+};
+void launch_surface_bwd(const SurfaceBwdArgs& a, cudaStream_t s);
+
 }  // namespace g4s

@@ -127,7 +127,7 @@ __device__ __forceinline__ void finite_differences(const SurfCam& c, float x, fl
 }
 
 // ---------------------------------------------------------------------------------------- forward
-__global__ void __launch_bounds__(SF_THREADS) surface_fwd_kernel(SurfaceFwdArgs a) {
+__global__ void __launch_bounds__(SF_THREADS, 4) surface_fwd_kernel(SurfaceFwdArgs a) {
     __shared__ SurfCam cam;
     if (threadIdx.x == 0) surface_camera(a.view, a.proj, a.W, a.H, &cam);
     __syncthreads();
@@ -183,7 +183,7 @@ constexpr int SB_GW = SF_TW + 2, SB_GH = SF_TH + 2;   // centre tile
 
 __device__ __forceinline__ float ld0(const float* p, size_t i) { return p ? p[i] : 0.0f; }
 
-__global__ void __launch_bounds__(SF_THREADS) surface_bwd_kernel(SurfaceBwdArgs a) {
+__global__ void __launch_bounds__(SF_THREADS, 4) surface_bwd_kernel(SurfaceBwdArgs a) {
     __shared__ SurfCam cam;
     __shared__ float s_depth[SB_DH][SB_DW];
     __shared__ float s_G[6][SB_GH * SB_GW];
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(SF_THREADS) surface_bwd_kernel(SurfaceBwdArgs 
             const float g_e = finite_f(quot) ? ld0(a.g_rend_depth, pix) + a.r0 * g_sd : 0.0f;
             const float inv_a = alpha != 0.0f ? 1.0f / alpha : 0.0f;
             const float g_D = g_e * inv_a;
-            const float g_alpha = ld0(a.g_rend_alpha, pix) - g_e * quot_or_zero(quot) * inv_a;
+            const float g_alpha = ld0(a.g_rend_alpha, pix) - (g_e != 0.0f ? g_e * quot * inv_a : 0.0f);
             const float g_med = finite_f(med) ? a.r1 * g_sd : 0.0f;
             const float w0 = ld0(a.g_rend_normal, pix), w1 = ld0(a.g_rend_normal, N + pix), w2 = ld0(a.g_rend_normal, 2 * N + pix);
             a.g_allmap[pix] = g_D;

@@ -136,6 +136,33 @@ int g4s_mark_visible(int P, const float* means3D, const float* viewmatrix, const
 int g4s_densify_stats(int P, const float* dL_dmeans2D, const int* radii, float* accum, float* denom,
                       int* max_radii, void* stream);
 
+/* ---- render() post-processing --------------------------------------------
+ * Replaces the ~15 torch kernels (and their autograd) that follow every rasterizer call in
+ * 2d-gaussian-splatting/gaussian_renderer/__init__.py:118-164 and utils/point_utils.py:9-37
+ * (depths_to_points, depth_to_normal): one kernel per direction, no host synchronisation (the
+ * reference inverts two matrices per call, which synchronises).
+ *   allmap[7,H,W]: the rasterizer's second image output; viewmatrix = world_view_transform[4,4],
+ *   projmatrix = full_proj_transform[4,4] (device, row-major as torch stores them);
+ *   depth_ratio = pipe.depth_ratio.
+ * Forward writes (device, caller-allocated):
+ *   rend_alpha[1,H,W] rend_normal[3,H,W] (world) rend_normal_cam[3,H,W] rend_dist[1,H,W]
+ *   surf_depth[1,H,W] surf_normal[3,H,W] (world, times alpha) surf_normal_cam[3,H,W] rend_depth[1,H,W]
+ * Backward: any upstream gradient pointer may be NULL (= zeros); dL_dallmap[7,H,W] is fully written.
+ * Where alpha == 0 the reference's autograd yields NaN for dL_dallmap[0:2] (0/0 in the division
+ * backward); those pixels have no contributor and the rasterizer ignores their gradients; here the
+ * masked terms contribute zero, so every written value is finite. */
+int g4s_surface_forward(int W, int H, const float* allmap, const float* viewmatrix,
+                        const float* projmatrix, double depth_ratio, float* rend_alpha,
+                        float* rend_normal, float* rend_normal_cam, float* rend_dist,
+                        float* surf_depth, float* surf_normal, float* surf_normal_cam,
+                        float* rend_depth, void* stream);
+int g4s_surface_backward(int W, int H, const float* allmap, const float* viewmatrix,
+                         const float* projmatrix, double depth_ratio, const float* dL_drend_alpha,
+                         const float* dL_drend_normal, const float* dL_drend_normal_cam,
+                         const float* dL_drend_dist, const float* dL_dsurf_depth,
+                         const float* dL_dsurf_normal, const float* dL_dsurf_normal_cam,
+                         const float* dL_drend_depth, float* dL_dallmap, void* stream);
+
 /* ---- introspection (tests, benchmarks) ----------------------------------------------------- */
 /* Copies decoded views of the opaque buffers into caller-provided DEVICE arrays (any may be
  * NULL).  Lets stage-level parity tests compare against the oracle without knowing the layout.
