@@ -276,6 +276,21 @@ int g4s_densify_stats(int P, const float* dL_dmeans2D, const int* radii, float* 
     return stage_check(false, (cudaStream_t)stream, "densify_stats");
 }
 
+int g4s_mip_filter(int P, const float* xyz, int num_cameras, const float* cameras, float znear, float focal_length,
+                   float sqrt_filter_variance, float* mip_filter, uint32_t* max_distance_bits, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P < 0 || num_cameras < 0) return fail(G4S_EINVAL, "g4s_mip_filter: bad P / num_cameras");
+    if (P == 0) return G4S_OK;
+    if (!xyz || !mip_filter || !max_distance_bits || (num_cameras > 0 && !cameras))
+        return fail(G4S_EINVAL, "g4s_mip_filter: null buffer");
+    if (!(focal_length > 0.0f)) return fail(G4S_EINVAL, "g4s_mip_filter: focal_length must be positive");
+    int rc;
+    if ((rc = check_cuda(cudaMemsetAsync(max_distance_bits, 0, sizeof(uint32_t), s), "memset max distance"))) return rc;
+    launch_mip_filter(P, xyz, num_cameras, cameras, znear, focal_length, sqrt_filter_variance, mip_filter,
+                      max_distance_bits, s);
+    return stage_check(false, s, "mip_filter");
+}
+
 int g4s_surface_forward(int W, int H, const float* allmap, const float* viewmatrix, const float* projmatrix,
                         double depth_ratio, float* rend_alpha, float* rend_normal, float* rend_normal_cam, float* rend_dist,
                         float* surf_depth, float* surf_normal, float* surf_normal_cam, float* rend_depth, void* stream) {

@@ -101,6 +101,10 @@ void launch_densify_stats(int P, const float* dL_dmeans2D, const int* radii, flo
                           int* max_radii, cudaStream_t s);
 void launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s);
 
+// ---- compute_mip_filter (gaussian_model.cu) ---------------------------------------------------
+void launch_mip_filter(int P, const float* xyz, int C, const float* cams, float znear, float focal_length,
+                       float sqrt_variance, float* filter, unsigned int* max_bits, cudaStream_t s);
+
 // ---- render() post-processing (surface.cu) ----------------------------------------------------
 struct SurfaceFwdArgs {
     int W, H;

@@ -136,6 +136,24 @@ int g4s_mark_visible(int P, const float* means3D, const float* viewmatrix, const
 int g4s_densify_stats(int P, const float* dL_dmeans2D, const int* radii, float* accum, float* denom,
                       int* max_radii, void* stream);
 
+/* ---- compute_mip_filter ------------------------------------------------------
+ * Replaces GaussianModel.compute_mip_filter (2DGS/scene/gaussian_model.py:388-434): a Python loop
+ * over ALL cameras with ~14 torch kernels each on [P]-sized tensors.  Two launches here.
+ *   cameras: DEVICE float[num_cameras][20] = { R[9] (camera.R row-major; xyz_cam = xyz @ R + T),
+ *            T[3], focal_x, focal_y, W/2, H/2, -0.15 W, 1.15 W, -0.15 H, 1.15 H }
+ *   focal_length = max over cameras of focal_x (the reference takes it on the host, :428-429)
+ *   sqrt_filter_variance = filter_variance ** 0.5
+ *   mip_filter[P] (output) = distance / focal_length * sqrt_filter_variance, distance = the smallest
+ *            clamped camera-space depth over the cameras that see the point (z > znear, projection
+ *            inside the image enlarged by 15 %), or the largest such distance of any point for
+ *            points no camera sees (:431).
+ *   max_distance_bits: DEVICE uint32 scratch; afterwards the fp32 bits of that largest distance,
+ *            0 when NO point is seen by any camera (the reference raises there: max() of an empty
+ *            tensor), mip_filter is then 0. */
+int g4s_mip_filter(int P, const float* xyz, int num_cameras, const float* cameras, float znear,
+                   float focal_length, float sqrt_filter_variance, float* mip_filter,
+                   uint32_t* max_distance_bits, void* stream);
+
 /* ---- render() post-processing --------------------------------------------
  * Replaces the ~15 torch kernels (and their autograd) that follow every rasterizer call in
  * 2d-gaussian-splatting/gaussian_renderer/__init__.py:118-164 and utils/point_utils.py:9-37

@@ -37,3 +37,19 @@ def oracle64():
     o = Oracle("f64")
     o.set_threads(1)
     return o
+
+
+@pytest.fixture(scope="session")
+def b200():
+    """The product operator module (loads libg4s_rasterizer.so; no fallback)."""
+    import g4splat_b200.diff_surfel_rasterization as op
+    return op
+
+
+@pytest.fixture(scope="session")
+def reference():
+    """The unmodified reference extension built into oracle/_ref (GPU side-by-side runs)."""
+    from oracle import build_ref
+    if not build_ref.up_to_date():
+        pytest.skip("oracle/_ref not built (no /root/reference here and no prebuilt files)")
+    return build_ref.import_reference()

@@ -26,20 +26,6 @@ FWD_BUDGET = 2e-4   # fraction of image elements allowed outside 1e-4 (threshold
 GRAD_BUDGET = 2e-4
 
 
-@pytest.fixture(scope="module")
-def b200():
-    import g4splat_b200.diff_surfel_rasterization as op
-    return op
-
-
-@pytest.fixture(scope="module")
-def reference():
-    from oracle import build_ref
-    if not build_ref.up_to_date():
-        pytest.skip("oracle/_ref not built (no /root/reference here and no prebuilt files)")
-    return build_ref.import_reference()
-
-
 SMALL = ["tiny", "scalemod", "c0_deg1", "ragged", "c0", "c0_bg", "c0_deg0", "c0_precomp"]
 
 

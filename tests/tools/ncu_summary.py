@@ -63,6 +63,15 @@ def full(tag, out):
         for k in KEYS:
             if k in idx:
                 out.append(f"| {k} | {r[idx[k]]} | {units[idx[k]]} |")
+        # which execution pipe the issue slots go to (fma / alu / xu / lsu ...)
+        for k in hdr:
+            if k not in KEYS and ("inst_executed_pipe_" in k or "_cycles_active" in k and "pipe_" in k) and \
+                    "pct_of_peak_sustained_active" in k and "tensor" not in k:
+                try:
+                    if float(r[idx[k]].replace(",", "")) >= 1.0:
+                        out.append(f"| {k} | {r[idx[k]]} | {units[idx[k]]} |")
+                except ValueError:
+                    pass
         out.append("")
 
 
