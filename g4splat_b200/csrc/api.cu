@@ -276,6 +276,26 @@ int g4s_densify_stats(int P, const float* dL_dmeans2D, const int* radii, float* 
     return stage_check(false, (cudaStream_t)stream, "densify_stats");
 }
 
+int g4s_photometric_forward(int W, int H, int C, const float* image, const float* gt, const float* window11,
+                            float lambda_dssim, double* sums, float* dmaps, float* out3, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (W <= 0 || H <= 0 || C <= 0 || C > 65535) return fail(G4S_EINVAL, "g4s_photometric_forward: bad W/H/C");
+    if (!image || !gt || !window11 || !sums || !out3) return fail(G4S_EINVAL, "g4s_photometric_forward: null buffer");
+    int rc;
+    if ((rc = check_cuda(cudaMemsetAsync(sums, 0, 2 * sizeof(double), s), "memset loss sums"))) return rc;
+    launch_photometric_fwd(W, H, C, image, gt, window11, lambda_dssim, sums, dmaps, out3, s);
+    return stage_check(false, s, "photometric_fwd");
+}
+
+int g4s_photometric_backward(int W, int H, int C, const float* image, const float* gt, const float* window11,
+                             float lambda_dssim, const float* dmaps, const float* dL_dloss, float* dL_dimage, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (W <= 0 || H <= 0 || C <= 0 || C > 65535) return fail(G4S_EINVAL, "g4s_photometric_backward: bad W/H/C");
+    if (!image || !gt || !window11 || !dmaps || !dL_dimage) return fail(G4S_EINVAL, "g4s_photometric_backward: null buffer");
+    launch_photometric_bwd(W, H, C, image, gt, window11, lambda_dssim, dmaps, dL_dloss, dL_dimage, s);
+    return stage_check(false, s, "photometric_bwd");
+}
+
 int g4s_mip_filter(int P, const float* xyz, int num_cameras, const float* cameras, float znear, float focal_length,
                    float sqrt_filter_variance, float* mip_filter, uint32_t* max_distance_bits, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;

@@ -105,6 +105,12 @@ void launch_mark_visible(int P, const float* means3D, const float* view, uint8_t
 void launch_mip_filter(int P, const float* xyz, int C, const float* cams, float znear, float focal_length,
                        float sqrt_variance, float* filter, unsigned int* max_bits, cudaStream_t s);
 
+// ---- photometric loss (loss.cu) ---------------------------------------------------------------
+void launch_photometric_fwd(int W, int H, int C, const float* img, const float* gt, const float* window11, float lambda,
+                            double* sums, float* dmaps, float* out3, cudaStream_t s);
+void launch_photometric_bwd(int W, int H, int C, const float* img, const float* gt, const float* window11, float lambda,
+                            const float* dmaps, const float* dL_dloss, float* dL_dimg, cudaStream_t s);
+
 // ---- render() post-processing (surface.cu) ----------------------------------------------------
 struct SurfaceFwdArgs {
     int W, H;

@@ -136,6 +136,26 @@ int g4s_mark_visible(int P, const float* means3D, const float* viewmatrix, const
 int g4s_densify_stats(int P, const float* dL_dmeans2D, const int* radii, float* accum, float* denom,
                       int* max_radii, void* stream);
 
+/* ---- photometric loss ---------------------------------------------------------
+ * Replaces what the trainer does with the rendered image every iteration
+ * (2DGS/train_with_refine_depth.py:382-383 with utils/loss_utils.py:17-18 l1_loss and :49-80 ssim):
+ *   loss = (1 - lambda_dssim) * mean|image - gt| + lambda_dssim * (1 - mean(ssim_map(image, gt)))
+ * -- five depthwise 11x11 conv2d launches, ~15 elementwise kernels and their autograd in the
+ * reference; one kernel per direction here (+ a one-thread finishing kernel).
+ *   image, gt: [C,H,W] fp32 (device).  window11: HOST float[11], the 1-D Gaussian of
+ *   loss_utils.gaussian(11, 1.5) (the reference's 2-D window is its outer product).
+ *   sums: DEVICE double[2] scratch (sum |x-y|, sum ssim).  out3: DEVICE float[3] = {loss, l1, ssim}.
+ *   dmaps: DEVICE float[3][C][H][W] written by the forward and read by the backward (the three
+ *   partial derivatives of the per-pixel ssim with respect to its window sums); NULL = forward only.
+ * Backward: dL_dloss = DEVICE float[1] upstream gradient of `loss` (NULL = 1); dL_dimage[C,H,W] is
+ * fully written.  Zero padding at the image border, like conv2d(padding=5). */
+int g4s_photometric_forward(int W, int H, int C, const float* image, const float* gt,
+                            const float* window11, float lambda_dssim, double* sums, float* dmaps,
+                            float* out3, void* stream);
+int g4s_photometric_backward(int W, int H, int C, const float* image, const float* gt,
+                             const float* window11, float lambda_dssim, const float* dmaps,
+                             const float* dL_dloss, float* dL_dimage, void* stream);
+
 /* ---- compute_mip_filter ------------------------------------------------------
  * Replaces GaussianModel.compute_mip_filter (2DGS/scene/gaussian_model.py:388-434): a Python loop
  * over ALL cameras with ~14 torch kernels each on [P]-sized tensors.  Two launches here.

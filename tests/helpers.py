@@ -210,3 +210,15 @@ def assert_parity(a: dict, b: dict, keys, rtol=1e-4, max_bad_frac=0.0, max_rel=N
             failures.append(f"{k}: max_rel {r['max_rel']:.3e} > {max_rel}")
     assert not failures, what + "\n" + "\n".join(failures) + "\n" + "\n".join(f"{k}: {v}" for k, v in rows.items())
     return rows
+
+
+# --------------------------------------------------------------------------------- golden files
+OTHER_STAGE_PREFIXES = ("surface_", "mip_filter_", "photometric_", "activations_")
+
+
+def rasterizer_golden_files():
+    """tests/golden/*.npz written by make_golden.py (the reference rasterizer extension on a B200); the
+    other stages' golden files carry their own prefixes."""
+    from pathlib import Path
+    d = Path(__file__).resolve().parent / "golden"
+    return sorted(p for p in d.glob("*.npz") if not p.name.startswith(OTHER_STAGE_PREFIXES))

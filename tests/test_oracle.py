@@ -70,7 +70,7 @@ def test_mark_visible(oracle32):
 
 
 def golden_files():
-    return sorted(p for p in GOLDEN.glob("*.npz") if not p.name.startswith("surface_"))
+    return Hh.rasterizer_golden_files()
 
 
 @pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.stem)

@@ -39,7 +39,7 @@ def test_b200_matches_oracle(name, b200, oracle32):
     assert Hh.radii_mismatch(got["radii"], want["radii"], loose=True) <= 3  # oracle is not FMA-exact; vs the reference it is 0
 
 
-@pytest.mark.parametrize("path", sorted(p for p in (ROOT / "tests" / "golden").glob("*.npz") if not p.name.startswith("surface_")), ids=lambda p: p.stem)
+@pytest.mark.parametrize("path", Hh.rasterizer_golden_files(), ids=lambda p: p.stem)
 def test_b200_matches_reference_golden(path, b200, oracle32):
     z = np.load(path)
     case = Hh.case_from_meta(json.loads(str(z["meta"])), oracle32)

@@ -1,0 +1,118 @@
+"""Times the caller-side rows of SURVEY.md 8(f) on the GPU, fused kernels against the reference's
+operator sequences (the torch restatements under oracle/ run on CUDA tensors = the kernels the
+reference launches):
+  * photometric loss (L1 + SSIM, forward + backward) at 3x1080x1920          -- loss_utils.py, train:382-383
+  * compute_mip_filter for 1.0 M Gaussians and 64 cameras                    -- gaussian_model.py:388-434
+
+    python tests/tools/bench_trainer_ops.py [--iters 30]      # prints one JSON line per row
+"""
+import argparse
+import json
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests" / "golden"))
+
+
+def timed(fn, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def bench_loss(iters):
+    import make_golden_loss as MG
+    from g4splat_b200.loss_utils import photometric_loss
+    from oracle import loss_oracle as LO
+    img_np, gt_np = MG.make_images(3, 1080, 1920, 7, "noisy")
+    img, gt = torch.tensor(img_np, device="cuda"), torch.tensor(gt_np, device="cuda")
+    grads = {}
+
+    def fused():
+        x = img.clone().requires_grad_(True)
+        loss, _ = photometric_loss(x, gt, 0.2)
+        loss.backward()
+        grads["fused"] = x.grad
+
+    def reference():
+        x = img.clone().requires_grad_(True)
+        loss = 0.8 * LO.l1_loss(x, gt) + 0.2 * (1.0 - LO.ssim(x, gt))
+        loss.backward()
+        grads["ref"] = x.grad
+
+    ms_f, ms_r = timed(fused, iters), timed(reference, iters)
+    err = float((grads["fused"] - grads["ref"]).abs().max() / grads["ref"].abs().max())
+    n = 3 * 1080 * 1920
+    alg = n * 4 * (2 + 3) + n * 4 * (3 + 2 + 1)     # fwd: read x, y, write 3 maps; bwd: read 3 maps, x, y, write grad
+    print(json.dumps({"row": "photometric loss (L1 + SSIM) forward + backward, 3x1080x1920", "fused_ms": ms_f,
+                      "reference_torch_ops_ms": ms_r, "speedup": ms_r / ms_f, "alg_bytes": alg,
+                      "fused_GBps": alg / (ms_f * 1e-3) / 1e9, "max_rel_grad_diff_vs_torch_fp32": err, "iters": iters}))
+
+
+def bench_mip(iters):
+    import make_golden_mip as MG
+    from g4splat_b200.gaussian_model import compute_mip_filter
+    from g4splat_b200 import synthetic as S
+    P, C = 1_000_000, 64
+    xyz = torch.tensor(S.make_scene(P, 2)["means3D"], device="cuda")
+    _, cams = MG.make_case(8, C, 1920, 1080, 3, 1.0)
+    out = {}
+
+    def fused():
+        out["fused"] = compute_mip_filter(xyz, cams)
+
+    def reference():                       # gaussian_model.py:388-434 on CUDA tensors
+        distance = torch.ones((P,), device="cuda") * 100000.0
+        valid_points = torch.zeros((P,), device="cuda", dtype=torch.bool)
+        focal_length = 0.0
+        for camera in cams:
+            R = torch.tensor(camera.R, device="cuda", dtype=torch.float32)
+            T = torch.tensor(camera.T, device="cuda", dtype=torch.float32)
+            xyz_cam = xyz @ R + T[None, :]
+            xyz_to_cam = torch.norm(xyz_cam, dim=1)  # noqa: F841  (computed and unused in the reference too)
+            valid_depth = xyz_cam[:, 2] > 0.2
+            x, y, z = xyz_cam[:, 0], xyz_cam[:, 1], xyz_cam[:, 2]
+            z = torch.clamp(z, min=0.001)
+            x = x / z * camera.focal_x + camera.image_width / 2.0
+            y = y / z * camera.focal_y + camera.image_height / 2.0
+            in_screen = torch.logical_and(torch.logical_and(x >= -0.15 * camera.image_width, x <= camera.image_width * 1.15),
+                                          torch.logical_and(y >= -0.15 * camera.image_height, y <= 1.15 * camera.image_height))
+            valid = torch.logical_and(valid_depth, in_screen)
+            distance[valid] = torch.min(distance[valid], z[valid])
+            valid_points = torch.logical_or(valid_points, valid)
+            if focal_length < camera.focal_x:
+                focal_length = camera.focal_x
+        distance[~valid_points] = distance[valid_points].max()
+        out["ref"] = (distance / focal_length * (0.2 ** 0.5))[..., None]
+
+    ms_f, ms_r = timed(fused, iters), timed(reference, max(3, iters // 5))
+    bad = float(((out["fused"] - out["ref"]).abs() > 2e-6 * out["ref"].abs()).float().mean())
+    alg = P * (12 + 4) + C * 80
+    print(json.dumps({"row": f"compute_mip_filter, {P} Gaussians x {C} cameras", "fused_ms": ms_f, "reference_torch_ops_ms": ms_r,
+                      "speedup": ms_r / ms_f, "alg_bytes": alg, "fused_GBps": alg / (ms_f * 1e-3) / 1e9,
+                      "fraction_outside_2e-6": bad, "iters": iters}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=30)
+    args = ap.parse_args()
+    bench_loss(args.iters)
+    bench_mip(args.iters)
+
+
+if __name__ == "__main__":
+    main()
