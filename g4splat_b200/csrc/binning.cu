@@ -130,13 +130,89 @@ __device__ __forceinline__ void bitonic_sort_ascending(KeyArray keys, int n) {
     }
 }
 
+// Lists of up to WARP_SORT_MAX entries (nearly all of them: the mean list holds ~160) are sorted by ONE
+// warp in registers: element e = r * 32 + lane lives in register r of its lane, compare-exchange
+// partners at distance < 32 are reached with a shuffle, larger distances are other registers of the
+// same lane.  No shared memory, no block barrier; eight tiles per CTA.  Padding keys are all-ones
+// (greater than any depth<<32|index key), so they stay behind the n real entries.
+constexpr int WARP_SORT_MAX = 256;
+
+template <int NREG>
+__device__ __forceinline__ void warp_bitonic_sort(unsigned long long (&key)[NREG], int lane) {
+    constexpr int N = NREG * 32;
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int jr = j >> 5;
+#pragma unroll
+                for (int r = 0; r < NREG; r++) {
+                    if ((r & jr) == 0) {
+                        const bool asc = (((r * 32) & k) == 0);     // bit of k lies in the register index (k >= 64 here)
+                        const unsigned long long x = key[r], y = key[r | jr];
+                        const bool swap = asc ? (x > y) : (x < y);
+                        key[r] = swap ? y : x;
+                        key[r | jr] = swap ? x : y;
+                    }
+                }
+            } else {
+                const bool lower = (lane & j) == 0;
+#pragma unroll
+                for (int r = 0; r < NREG; r++) {
+                    const bool asc = (k >= 64) ? (((r * 32) & k) == 0) : ((lane & k) == 0);
+                    const unsigned long long x = key[r];
+                    const unsigned long long y = __shfl_xor_sync(0xffffffffu, x, j);
+                    const bool want_min = (lower == asc);
+                    key[r] = want_min ? (x < y ? x : y) : (x > y ? x : y);
+                }
+            }
+        }
+    }
+}
+
+template <int NREG>
+__device__ __forceinline__ void warp_sort_tile(const unsigned long long* __restrict__ gk, uint32_t* __restrict__ out,
+                                               int n, int lane) {
+    unsigned long long key[NREG];
+#pragma unroll
+    for (int r = 0; r < NREG; r++) {
+        const int e = r * 32 + lane;
+        key[r] = e < n ? gk[e] : ~0ull;
+    }
+    warp_bitonic_sort<NREG>(key, lane);
+#pragma unroll
+    for (int r = 0; r < NREG; r++) {
+        const int e = r * 32 + lane;
+        if (e < n) out[e] = (uint32_t)key[r];
+    }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) tile_sort_warp_kernel(TileSortArgs a) {
+    if ((int64_t)a.counters[CNT_RENDERED] > a.capacity) return;
+    const int slot = blockIdx.x * (SORT_THREADS / 32) + (threadIdx.x >> 5);
+    if (slot >= a.num_tiles) return;
+    const int lane = threadIdx.x & 31;
+    const int tile = (int)a.tile_order[slot];
+    const uint32_t off = a.tile_offset[tile];
+    const int n = (int)(a.tile_offset[tile + 1] - off);
+    if (n == 0 || n > WARP_SORT_MAX) return;
+    const unsigned long long* gk = a.keys + off;
+    uint32_t* out = a.list + off;
+    if (n <= 32) warp_sort_tile<1>(gk, out, n, lane);
+    else if (n <= 64) warp_sort_tile<2>(gk, out, n, lane);
+    else if (n <= 128) warp_sort_tile<4>(gk, out, n, lane);
+    else warp_sort_tile<8>(gk, out, n, lane);
+}
+
+// Lists longer than WARP_SORT_MAX: one CTA per tile, in shared memory.
 __global__ void __launch_bounds__(SORT_THREADS) tile_sort_kernel(TileSortArgs a) {
     if ((int64_t)a.counters[CNT_RENDERED] > a.capacity) return;
     extern __shared__ unsigned long long s_keys[];
     const int tile = (int)a.tile_order[blockIdx.x];
     const uint32_t off = a.tile_offset[tile];
     const int n = (int)(a.tile_offset[tile + 1] - off);
-    if (n == 0) return;
+    if (n <= WARP_SORT_MAX) return;
     unsigned long long* gk = a.keys + off;
     if (n <= SORT_SMEM_KEYS) {
         for (int i = threadIdx.x; i < n; i += SORT_THREADS) s_keys[i] = gk[i];
@@ -157,7 +233,11 @@ void launch_tile_scan(const TileScanArgs& a, cudaStream_t s) {
 }
 void launch_tile_sort(const TileSortArgs& a, cudaStream_t s) {
     if (a.num_tiles <= 0) return;
+    // long lists first (they sit at the front of tile_order), then everything else by warps
     tile_sort_kernel<<<a.num_tiles, SORT_THREADS, SORT_SMEM_KEYS * sizeof(unsigned long long), s>>>(a);
+    count_launch();
+    const int warps_per_cta = SORT_THREADS / 32;
+    tile_sort_warp_kernel<<<(a.num_tiles + warps_per_cta - 1) / warps_per_cta, SORT_THREADS, 0, s>>>(a);
     count_launch();
 }
 

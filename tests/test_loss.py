@@ -62,7 +62,7 @@ def _run_kernels(img, gt, lam, upstream=1.0):
     x = torch.tensor(img, device="cuda", requires_grad=True)
     loss, Ll1 = photometric_loss(x, torch.tensor(gt, device="cuda"), lam)
     (loss * upstream).backward()
-    return float(loss), float(Ll1), x.grad.cpu().numpy()
+    return float(loss.detach()), float(Ll1), x.grad.cpu().numpy()
 
 
 @pytest.mark.gpu

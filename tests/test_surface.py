@@ -148,13 +148,20 @@ def test_kernels_full_size_against_fp64(b200, oracle32):
     rng = np.random.default_rng(9)
     up = {k: np.float32(rng.normal(size=(c, cam.H, cam.W)) / (cam.W * cam.H))
           for k, c in zip(SO.KEYS, (1, 3, 3, 1, 1, 3, 3, 1))}
+    # surf_normal differentiates surf_depth numerically.  With depth_ratio < 1 that depth holds the
+    # quotient allmap[0] / alpha, which every fp32 implementation (the reference included) rounds to
+    # fp32 before differencing: 0.5 ulp of a ~2.5 m depth against a ~1 mm pixel-to-pixel step is ~1e-4
+    # of the normal, whatever the kernel does afterwards.  The fp64 oracle divides in fp64, so the
+    # normals (and the gradient that flows through them) get 3e-4 at this size; everything else 2e-5.
+    loose = ("surf_normal", "surf_normal_cam", "dL_dallmap")
     for ratio in (0.0, 1.0):
         got = _run_kernels(out["allmap"], cam.viewmatrix, cam.projmatrix, ratio, up)
         o64 = SO.run(out["allmap"], cam.viewmatrix, cam.projmatrix, ratio, up, np.float64)
         for k in ALL:
             finite = np.isfinite(o64[k])
             assert np.isfinite(got[k]).all(), k
-            assert _rel(got[k], o64[k], finite) < 2e-5, (ratio, k, _rel(got[k], o64[k], finite))
+            tol = 3e-4 if (k in loose and ratio < 1.0) else 2e-5
+            assert _rel(got[k], o64[k], finite) < tol, (ratio, k, _rel(got[k], o64[k], finite))
     torch.cuda.synchronize()
 
 
