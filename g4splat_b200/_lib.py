@@ -24,6 +24,11 @@ SIGNATURES = {
     "g4s_forward_render": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i]),
     "g4s_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _f, _f,
                           _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i]),
+    "g4s_backward_scratch_bytes_raw": (_sz, [_i]),
+    "g4s_forward_plan_raw": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp,
+                                  _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _i]),
+    "g4s_backward_raw": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _f, _f,
+                              _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i]),
     "g4s_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
     "g4s_densify_stats": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4s_photometric_forward": (_i, [_i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp]),

@@ -97,14 +97,20 @@ size_t g4s_geom_bytes(int P) { return geom_layout(P, nullptr, nullptr); }
 size_t g4s_image_bytes(int W, int H) { return image_layout(W, H, nullptr, nullptr); }
 size_t g4s_binning_bytes(int64_t capacity) { return bin_layout(capacity, nullptr, nullptr); }
 size_t g4s_backward_scratch_bytes(int P) { return align_up((size_t)(P > 0 ? P : 1) * ACC_FLOATS * sizeof(float), 256); }
+size_t g4s_backward_scratch_bytes_raw(int P) {
+    return g4s_backward_scratch_bytes(P) + align_up((size_t)(P > 0 ? P : 1) * (3 + 9) * sizeof(float), 256);
+}
 
-int g4s_forward_plan(int P, int D, int M, int W, int H, const float* means3D, const float* shs,
-                     const float* colors_precomp, const float* opacities, const float* scales,
-                     float scale_modifier, const float* rotations, const float* transMat_precomp,
-                     const float* viewmatrix, const float* projmatrix, const float* cam_pos,
-                     float tan_fovx, float tan_fovy, int prefiltered, int* radii, void* geom_buffer,
-                     void* img_buffer, int32_t* host_counts, void* stream, int debug) {
-    (void)tan_fovx; (void)tan_fovy;
+}  // extern "C"
+
+// raw != 0: shs = _features_dc, sh_rest = _features_rest, opacities / scales / rotations before activation
+static int forward_plan_impl(int P, int D, int M, int W, int H, const float* means3D, const float* shs,
+                             const float* colors_precomp, const float* opacities, const float* scales,
+                             float scale_modifier, const float* rotations, const float* transMat_precomp,
+                             const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                             int prefiltered, int* radii, void* geom_buffer,
+                             void* img_buffer, int32_t* host_counts, void* stream, int debug,
+                             int raw, const float* sh_rest, const float* mip_filter) {
     cudaStream_t s = (cudaStream_t)stream;
     if (P < 0 || W <= 0 || H <= 0) return fail(G4S_EINVAL, "g4s_forward_plan: bad P/W/H");
     if (!img_buffer || !geom_buffer) return fail(G4S_EINVAL, "g4s_forward_plan: null scratch buffer");
@@ -138,6 +144,7 @@ int g4s_forward_plan(int P, int D, int M, int W, int H, const float* means3D, co
     pa.scales = scales; pa.scale_modifier = scale_modifier; pa.rotations = rotations; pa.transMat_precomp = transMat_precomp;
     pa.view = viewmatrix; pa.proj = projmatrix; pa.campos = cam_pos;
     pa.radii = radii; pa.geom = geom; pa.tile_count = img.tile_count; pa.counters = img.counters;
+    pa.raw = raw; pa.sh_rest = sh_rest; pa.mip_filter = mip_filter;
     { StageTimer tm(ST_PROJECT_FWD, s); launch_project_fwd(pa, s); }
     if ((rc = stage_check(debug, s, "project_fwd"))) return rc;
 
@@ -158,6 +165,36 @@ int g4s_forward_plan(int P, int D, int M, int W, int H, const float* means3D, co
             return fail(G4S_ECUDA, "Point is filtered although prefiltered is set. This shouldn't happen!");
     }
     return G4S_OK;
+}
+
+extern "C" {
+
+int g4s_forward_plan(int P, int D, int M, int W, int H, const float* means3D, const float* shs,
+                     const float* colors_precomp, const float* opacities, const float* scales,
+                     float scale_modifier, const float* rotations, const float* transMat_precomp,
+                     const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                     float tan_fovx, float tan_fovy, int prefiltered, int* radii, void* geom_buffer,
+                     void* img_buffer, int32_t* host_counts, void* stream, int debug) {
+    (void)tan_fovx; (void)tan_fovy;
+    return forward_plan_impl(P, D, M, W, H, means3D, shs, colors_precomp, opacities, scales, scale_modifier, rotations,
+                             transMat_precomp, viewmatrix, projmatrix, cam_pos, prefiltered, radii, geom_buffer,
+                             img_buffer, host_counts, stream, debug, 0, nullptr, nullptr);
+}
+
+int g4s_forward_plan_raw(int P, int D, int M, int W, int H, const float* xyz, const float* features_dc,
+                         const float* features_rest, const float* opacity_raw, const float* scaling_raw,
+                         float scale_modifier, const float* rotation_raw, const float* mip_filter,
+                         const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                         float tan_fovx, float tan_fovy, int prefiltered, int* radii, void* geom_buffer,
+                         void* img_buffer, int32_t* host_counts, void* stream, int debug) {
+    (void)tan_fovx; (void)tan_fovy;
+    if (P > 0) {
+        if (!features_dc || !scaling_raw || !rotation_raw) return fail(G4S_EINVAL, "g4s_forward_plan_raw: null parameter tensor");
+        if (M < 1 || (M > 1 && !features_rest)) return fail(G4S_EINVAL, "g4s_forward_plan_raw: features_rest required when M > 1");
+    }
+    return forward_plan_impl(P, D, M, W, H, xyz, features_dc, nullptr, opacity_raw, scaling_raw, scale_modifier, rotation_raw,
+                             nullptr, viewmatrix, projmatrix, cam_pos, prefiltered, radii, geom_buffer, img_buffer,
+                             host_counts, stream, debug, 1, features_rest, mip_filter);
 }
 
 int g4s_forward_render(int P, int W, int H, const float* background, const void* geom_buffer,
@@ -202,16 +239,18 @@ int g4s_forward_render(int P, int W, int H, const float* background, const void*
     return stage_check(debug, s, "blend_fwd");
 }
 
-int g4s_backward(int P, int D, int M, int W, int H, const float* background, const float* means3D,
-                 const float* shs, const float* colors_precomp, const float* scales, float scale_modifier,
-                 const float* rotations, const float* transMat_precomp, const float* viewmatrix,
-                 const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
-                 const int* radii, const void* geom_buffer, const void* binning_buffer, int64_t capacity,
-                 const void* img_buffer, const float* dL_dout_color, const float* dL_dout_others,
-                 float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors,
-                 float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dtransMat,
-                 int accumulate_mask, void* scratch, void* stream, int debug) {
-    (void)scale_modifier; (void)colors_precomp; (void)transMat_precomp;
+}  // extern "C"
+
+static int backward_impl(int P, int D, int M, int W, int H, const float* background, const float* means3D,
+                         const float* shs, const float* scales,
+                         const float* rotations, const float* viewmatrix,
+                         const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
+                         const int* radii, const void* geom_buffer, const void* binning_buffer, int64_t capacity,
+                         const void* img_buffer, const float* dL_dout_color, const float* dL_dout_others,
+                         float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors,
+                         float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dtransMat,
+                         int accumulate_mask, void* scratch, void* stream, int debug,
+                         int raw, const float* sh_rest, const float* opacity_raw, const float* mip_filter, float* dL_dsh_rest) {
     cudaStream_t s = (cudaStream_t)stream;
     if (P < 0 || W <= 0 || H <= 0 || capacity < 0) return fail(G4S_EINVAL, "g4s_backward: bad sizes");
     if (P == 0) return G4S_OK;
@@ -253,8 +292,52 @@ int g4s_backward(int P, int D, int M, int W, int H, const float* background, con
     pb.dL_dmeans3D = dL_dmeans3D; pb.dL_dmeans2D = dL_dmeans2D; pb.dL_dsh = (M > 0 && shs) ? dL_dsh : nullptr;
     pb.dL_dcolors = dL_dcolors; pb.dL_dopacity = dL_dopacity; pb.dL_dscales = dL_dscales; pb.dL_drots = dL_drotations;
     pb.dL_dtransMat = dL_dtransMat;
+    pb.raw = raw; pb.sh_rest = sh_rest; pb.opacities = opacity_raw; pb.mip_filter = mip_filter; pb.dL_dsh_rest = dL_dsh_rest;
     { StageTimer tm(ST_PROJECT_BWD, s); launch_project_bwd(pb, s); }
     return stage_check(debug, s, "project_bwd");
+}
+
+extern "C" {
+
+int g4s_backward(int P, int D, int M, int W, int H, const float* background, const float* means3D,
+                 const float* shs, const float* colors_precomp, const float* scales, float scale_modifier,
+                 const float* rotations, const float* transMat_precomp, const float* viewmatrix,
+                 const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
+                 const int* radii, const void* geom_buffer, const void* binning_buffer, int64_t capacity,
+                 const void* img_buffer, const float* dL_dout_color, const float* dL_dout_others,
+                 float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors,
+                 float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dtransMat,
+                 int accumulate_mask, void* scratch, void* stream, int debug) {
+    (void)scale_modifier; (void)colors_precomp; (void)transMat_precomp;
+    if (P > 0 && (!dL_dmeans3D || !dL_dmeans2D || !dL_dcolors || !dL_dopacity || !dL_dscales || !dL_drotations || !dL_dtransMat))
+        return fail(G4S_EINVAL, "g4s_backward: null buffer");
+    return backward_impl(P, D, M, W, H, background, means3D, shs, scales, rotations, viewmatrix, projmatrix, cam_pos,
+                         tan_fovx, tan_fovy, radii, geom_buffer, binning_buffer, capacity, img_buffer, dL_dout_color,
+                         dL_dout_others, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales,
+                         dL_drotations, dL_dtransMat, accumulate_mask, scratch, stream, debug, 0, nullptr, nullptr, nullptr, nullptr);
+}
+
+int g4s_backward_raw(int P, int D, int M, int W, int H, const float* background, const float* xyz,
+                     const float* features_dc, const float* features_rest, const float* opacity_raw,
+                     const float* scaling_raw, float scale_modifier, const float* rotation_raw,
+                     const float* mip_filter, const float* viewmatrix, const float* projmatrix,
+                     const float* cam_pos, float tan_fovx, float tan_fovy, const int* radii,
+                     const void* geom_buffer, const void* binning_buffer, int64_t capacity, const void* img_buffer,
+                     const float* dL_dout_color, const float* dL_dout_others, float* dL_dxyz, float* dL_dmeans2D,
+                     float* dL_dfeatures_dc, float* dL_dfeatures_rest, float* dL_dopacity_raw, float* dL_dscaling_raw,
+                     float* dL_drotation_raw, int accumulate_mask, void* scratch, void* stream, int debug) {
+    (void)scale_modifier;
+    if (P > 0 && (!features_dc || !opacity_raw || !scaling_raw || !rotation_raw || !dL_dxyz || !dL_dmeans2D || !dL_dfeatures_dc ||
+                  !dL_dopacity_raw || !dL_dscaling_raw || !dL_drotation_raw || (M > 1 && (!features_rest || !dL_dfeatures_rest))))
+        return fail(G4S_EINVAL, "g4s_backward_raw: null buffer");
+    // the operator-only outputs (dL_dcolors_precomp, dL_dtransMat) have no raw counterpart: the tail of the
+    // scratch buffer takes them (g4s_backward_scratch_bytes_raw)
+    float* spill = P > 0 ? (float*)((char*)scratch + g4s_backward_scratch_bytes(P)) : nullptr;
+    return backward_impl(P, D, M, W, H, background, xyz, features_dc, scaling_raw, rotation_raw, viewmatrix, projmatrix, cam_pos,
+                         tan_fovx, tan_fovy, radii, geom_buffer, binning_buffer, capacity, img_buffer, dL_dout_color,
+                         dL_dout_others, dL_dxyz, dL_dmeans2D, dL_dfeatures_dc, spill, dL_dopacity_raw, dL_dscaling_raw,
+                         dL_drotation_raw, spill ? spill + (size_t)3 * P : nullptr, accumulate_mask, scratch, stream, debug,
+                         1, features_rest, opacity_raw, mip_filter, dL_dfeatures_rest);
 }
 
 int g4s_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,

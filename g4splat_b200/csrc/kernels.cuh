@@ -8,6 +8,9 @@ void count_launch();  // bumps the process-wide launch counter (api.cu)
 
 struct ProjectArgs {
     int P, D, M, W, H, grid_x, grid_y, prefiltered;
+    // raw != 0: the trainer's parameters before activation: shs = _features_dc [P,1,3],
+    // sh_rest = _features_rest [P,M-1,3], opacities / scales / rotations un-activated, mip_filter [P] or null
+    int raw; const float* sh_rest; const float* mip_filter;
     const float* means3D; const float* shs; const float* colors_precomp; const float* opacities;
     const float* scales; float scale_modifier; const float* rotations; const float* transMat_precomp;
     const float* view; const float* proj; const float* campos;
@@ -85,6 +88,7 @@ void launch_blend_bwd(const BlendBwdArgs& a, cudaStream_t s);
 enum { ACC_MEANS3D = 1, ACC_SH = 2, ACC_OPACITY = 4, ACC_SCALES = 8, ACC_ROTATIONS = 16 };
 struct ProjectBwdArgs {
     int P, D, M;
+    int raw; const float* sh_rest; const float* opacities; const float* mip_filter; float* dL_dsh_rest;  // see ProjectArgs
     int accumulate;  // ACC_* bits: add into that output (visible rows only) instead of overwriting it
     const float* means3D; const float* shs; const float* scales; const float* rotations;
     const float* view; const float* proj; const float* campos;

@@ -27,11 +27,14 @@ __device__ const float SH_C3[] = {-0.5900435899266435f, 2.890611442640554f, -0.4
 // Degree-D real SH -> RGB for one Gaussian, + 0.5, clamp at 0 (CR/forward.cu:20-71).  Rounding pinned
 // to the reference's SASS: every term is accumulated with one fma(coef, sh, r); the coefficients are
 // rounded products, with xx*3 - yy, zz*4 - xx, 2zz - 3xx - 3yy and xx - 3yy fused as fma(.., +-3|4, ..).
-__device__ __forceinline__ f3 sh_to_rgb(int deg, const float* __restrict__ sh /* [M][3] */, f3 dir,
+// Coefficient 0 is read from `sh0`, coefficients i >= 1 from `shr[3 (i - 1) ..]`: one [M][3] array
+// (shr = sh0 + 3) for the operator API, the trainer's separate _features_dc / _features_rest tensors
+// for the raw-parameter entry points.
+__device__ __forceinline__ f3 sh_to_rgb(int deg, const float* __restrict__ sh0, const float* __restrict__ shr, f3 dir,
                                         uint8_t& clamp_mask) {
-    f3 r = mk3(__fmul_rn(SH_C0, sh[0]), __fmul_rn(SH_C0, sh[1]), __fmul_rn(SH_C0, sh[2]));
+    f3 r = mk3(__fmul_rn(SH_C0, sh0[0]), __fmul_rn(SH_C0, sh0[1]), __fmul_rn(SH_C0, sh0[2]));
     auto acc = [&](float k, int i) {
-        r.x = __fmaf_rn(k, sh[3 * i], r.x); r.y = __fmaf_rn(k, sh[3 * i + 1], r.y); r.z = __fmaf_rn(k, sh[3 * i + 2], r.z);
+        r.x = __fmaf_rn(k, shr[3 * i - 3], r.x); r.y = __fmaf_rn(k, shr[3 * i - 2], r.y); r.z = __fmaf_rn(k, shr[3 * i - 1], r.z);
     };
     if (deg > 0) {
         const float x = dir.x, y = dir.y, z = dir.z;
@@ -127,6 +130,46 @@ __device__ __forceinline__ bool contribution_bbox(f3 Tu, f3 Tv, f3 Tw, float cx,
     return true;
 }
 
+// Parameter activations of the trainer (2DGS/scene/gaussian_model.py:158-192), applied in registers by
+// the raw-parameter entry points instead of ~10 torch kernels per call:
+//   scaling  = exp(_scaling)                       [+ mip filter: sqrt(scaling^2 + filter^2)]
+//   rotation = _rotation / max(|_rotation|, 1e-12) (torch.nn.functional.normalize)
+//   opacity  = sigmoid(_opacity)                   [+ mip filter: * sqrt(det1 / det2),
+//              det1 = prod exp(_scaling)^2, det2 = prod (exp(_scaling)^2 + filter^2)]
+// Each operation is rounded where torch rounds it (one kernel per operator there).
+struct Activated {
+    float2 scale;      // activated scaling
+    float2 e2;         // exp(_scaling)^2
+    float4 rot;        // normalised rotation
+    float inv_norm;    // 1 / max(|_rotation|, eps)
+    float opacity, sig, coef, f2;   // activated opacity = sig * coef; f2 = filter^2 (0 without mip filter)
+};
+__device__ __forceinline__ Activated activate(float2 s_raw, float4 r_raw, float o_raw, const float* mip_filter, int idx) {
+    Activated a;
+    const float e0 = expf(s_raw.x), e1 = expf(s_raw.y);
+    a.e2 = make_float2(__fmul_rn(e0, e0), __fmul_rn(e1, e1));
+    a.sig = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-o_raw)));
+    if (mip_filter != nullptr) {
+        const float f = mip_filter[idx];
+        a.f2 = __fmul_rn(f, f);
+        const float d0 = __fadd_rn(a.e2.x, a.f2), d1 = __fadd_rn(a.e2.y, a.f2);
+        a.scale = make_float2(__fsqrt_rn(d0), __fsqrt_rn(d1));
+        a.coef = __fsqrt_rn(__fdiv_rn(__fmul_rn(a.e2.x, a.e2.y), __fmul_rn(d0, d1)));
+        a.opacity = __fmul_rn(a.sig, a.coef);
+    } else {
+        a.f2 = 0.0f;
+        a.scale = make_float2(e0, e1);
+        a.coef = 1.0f;
+        a.opacity = a.sig;
+    }
+    const float n2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r_raw.x, r_raw.x), __fmul_rn(r_raw.y, r_raw.y)),
+                                         __fmul_rn(r_raw.z, r_raw.z)), __fmul_rn(r_raw.w, r_raw.w));
+    const float n = fmaxf(__fsqrt_rn(n2), 1e-12f);
+    a.inv_norm = __fdiv_rn(1.0f, n);
+    a.rot = make_float4(__fdiv_rn(r_raw.x, n), __fdiv_rn(r_raw.y, n), __fdiv_rn(r_raw.z, n), __fdiv_rn(r_raw.w, n));
+    return a;
+}
+
 // Per-thread part of the forward projection.  Returns false when the Gaussian is culled (radii 0).
 struct ProjOut {
     f3 Tu, Tv, Tw, normal, rgb;
@@ -136,6 +179,7 @@ struct ProjOut {
     int radius, rx0, ry0, rx1, ry1;   // candidate tile rectangle: reference rect x contribution bbox (may be empty)
     uint8_t clamp_mask;
 };
+template <bool RAW>
 __device__ __forceinline__ bool project_one(const ProjectArgs& a, int idx, ProjOut& o) {
     const f3 p = mk3(a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]);
     const f3 pv = xform_point_4x3(p, a.view);
@@ -144,9 +188,14 @@ __device__ __forceinline__ bool project_one(const ProjectArgs& a, int idx, ProjO
         return false;
     }
     f3 Tu, Tv, Tw, normal;
+    float opacity_act = 0.0f;
     if (a.transMat_precomp == nullptr) {
-        const float2 sc = ((const float2*)a.scales)[idx];
-        const float4 q = ((const float4*)a.rotations)[idx];
+        float2 sc = ((const float2*)a.scales)[idx];
+        float4 q = ((const float4*)a.rotations)[idx];
+        if (RAW) {
+            const Activated act = activate(sc, q, a.opacities[idx], a.mip_filter, idx);
+            sc = act.scale; q = act.rot; opacity_act = act.opacity;
+        }
         f3 R[3];
         quat_to_R(q, R);
         build_T(p, __fmul_rn(a.scale_modifier, sc.x), __fmul_rn(a.scale_modifier, sc.y), R, a.proj, a.W, a.H, Tu, Tv, Tw);
@@ -195,11 +244,16 @@ __device__ __forceinline__ bool project_one(const ProjectArgs& a, int idx, ProjO
         f3 dir = sub3(p, mk3(a.campos[0], a.campos[1], a.campos[2]));
         const float len = __fsqrt_rn(dot3_rn(dir.x, dir.x, dir.y, dir.y, dir.z, dir.z));
         dir = mk3(__fdiv_rn(dir.x, len), __fdiv_rn(dir.y, len), __fdiv_rn(dir.z, len));
-        o.rgb = sh_to_rgb(a.D, a.shs + (size_t)idx * a.M * 3, dir, o.clamp_mask);
+        if (RAW) {
+            o.rgb = sh_to_rgb(a.D, a.shs + (size_t)idx * 3, a.sh_rest + (size_t)idx * (a.M - 1) * 3, dir, o.clamp_mask);
+        } else {
+            const float* sh = a.shs + (size_t)idx * a.M * 3;
+            o.rgb = sh_to_rgb(a.D, sh, sh + 3, dir, o.clamp_mask);
+        }
     } else {
         o.rgb = mk3(a.colors_precomp[3 * idx], a.colors_precomp[3 * idx + 1], a.colors_precomp[3 * idx + 2]);
     }
-    o.opacity = a.opacities[idx];
+    o.opacity = RAW ? opacity_act : a.opacities[idx];
 
     // exact culling, step 1: tiles of the reference rectangle that hold a pixel of the contribution bbox
     const bool can_contribute = contribution_bbox(Tu, Tv, Tw, cx, cy, o.opacity, o.bb, o.conic, o.conic_By, o.rr2);
@@ -223,12 +277,13 @@ __device__ __forceinline__ bool project_one(const ProjectArgs& a, int idx, ProjO
 // Gaussian of the warp in turn, the 32 lanes take 32 tiles of its rectangle, so long rectangles
 // (close-up splats cover thousands of tiles) do not serialise on one thread, and the surviving-
 // tile mask of small rectangles is simply the ballot.
+template <bool RAW>
 __global__ void __launch_bounds__(256) project_fwd_kernel(ProjectArgs a) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     ProjOut o;
     o.rx0 = o.ry0 = o.rx1 = o.ry1 = 0;
-    const bool visible = idx < a.P && project_one(a, idx, o);
+    const bool visible = idx < a.P && project_one<RAW>(a, idx, o);
     const int gx = a.grid_x;
     const int my_w = o.rx1 - o.rx0, my_total = visible ? my_w * (o.ry1 - o.ry0) : 0;
     // per-tile counters.  Rectangles of up to 32 tiles are counted by their own lane (fire-and-forget
@@ -307,13 +362,13 @@ __global__ void __launch_bounds__(256) scatter_kernel(ScatterArgs a) {
 // ---------------------------------------------------------------------------------------------
 // Backward of the SH colour (CR/backward.cu:20-139): writes dL_dsh[idx][k] for k < (D+1)^2 and
 // zeros above, returns the view-direction term to add to dL_dmean3D.
-__device__ __forceinline__ f3 sh_backward(int deg, int M, const float* __restrict__ sh, f3 dir_orig,
+__device__ __forceinline__ f3 sh_backward(int deg, int M, const float* __restrict__ shr /* coefficients 1.. */, f3 dir_orig,
                                           uint8_t clamp_mask, f3 dL_dcolor, float* __restrict__ dsh) {
     const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
     const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
     f3 g = mk3(dL_dcolor.x * ((clamp_mask & 1) ? 0.f : 1.f), dL_dcolor.y * ((clamp_mask & 2) ? 0.f : 1.f),
                dL_dcolor.z * ((clamp_mask & 4) ? 0.f : 1.f));
-    auto c = [&](int k) { return mk3(sh[3 * k], sh[3 * k + 1], sh[3 * k + 2]); };
+    auto c = [&](int k) { return mk3(shr[3 * k - 3], shr[3 * k - 2], shr[3 * k - 1]); };   // k >= 1 only
     auto put = [&](int k, float v) { dsh[3 * k] = v * g.x; dsh[3 * k + 1] = v * g.y; dsh[3 * k + 2] = v * g.z; };
     auto axpy = [&](f3& acc, float s, f3 v) { acc.x += s * v.x; acc.y += s * v.y; acc.z += s * v.z; };
     f3 dx = mk3(0, 0, 0), dy = mk3(0, 0, 0), dz = mk3(0, 0, 0);
@@ -372,6 +427,7 @@ constexpr int PB_SMALL = 25;      // means3D 3, means2D 3, colors 3, opacity 1, 
 constexpr int PB_MAX_M = 16;
 constexpr int PB_SH_STRIDE = PB_MAX_M * 3 + 1;   // odd row stride: conflict-free per-thread writes
 
+template <bool RAW>
 __global__ void __launch_bounds__(PB_THREADS) project_bwd_kernel(ProjectBwdArgs a) {
     __shared__ float s_sh[PB_WARPS][32 * PB_SH_STRIDE];
     __shared__ float s_small[PB_WARPS][32 * PB_SMALL];
@@ -412,11 +468,17 @@ __global__ void __launch_bounds__(PB_THREADS) project_bwd_kernel(ProjectBwdArgs 
         float sx = 0, sy = 0;
         float Pm[3][4];
         float4 quat = make_float4(1, 0, 0, 0);
+        Activated act;
+        act.inv_norm = 1.0f;
         if (precomp) {
             Tu = mk3(q1.x, q1.y, q1.z); Tv = mk3(q1.w, q2.x, q2.y); Tw = mk3(q2.z, q2.w, q3.x);
         } else {
-            const float2 sc = ((const float2*)a.scales)[idx];
+            float2 sc = ((const float2*)a.scales)[idx];
             quat = ((const float4*)a.rotations)[idx];
+            if (RAW) {
+                act = activate(sc, quat, a.opacities[idx], a.mip_filter, idx);
+                sc = act.scale; quat = act.rot;
+            }
             sx = sc.x; sy = sc.y;  // scale_modifier ignored on purpose (quirk 2, CR/backward.cu:481)
             quat_to_R(quat, R);
             // P = world2ndc * ndc2pix (mat3x4), T = transpose(M) * P (CR/backward.cu:490-504)
@@ -496,8 +558,28 @@ __global__ void __launch_bounds__(PB_THREADS) project_bwd_kernel(ProjectBwdArgs 
         }
         if (a.shs) {
             const f3 dir = sub3(p, mk3(a.campos[0], a.campos[1], a.campos[2]));
-            const f3 dmean = sh_backward(a.D, M, a.shs + (size_t)idx * M * 3, dir, a.geom.clamped[idx], dcol, my_sh);
+            const float* shr = RAW ? a.sh_rest + (size_t)idx * (M - 1) * 3 : a.shs + (size_t)idx * M * 3 + 3;
+            const f3 dmean = sh_backward(a.D, M, shr, dir, a.geom.clamped[idx], dcol, my_sh);
             my[0] += dmean.x; my[1] += dmean.y; my[2] += dmean.z;
+        }
+        if (RAW && !precomp) {
+            // chain rule through the activations (what autograd does after the reference operator):
+            //   exp:        d/d_scaling = g e            [mip: scale = sqrt(e^2 + f^2): g e^2 / scale,
+            //               plus the opacity's dependence on the scales: g_o opacity f^2 / (e^2 + f^2)]
+            //   sigmoid:    d/d_opacity = g_o coef sig (1 - sig)
+            //   normalize:  d/d_rotation = (g - q (q . g)) / max(|r|, eps)
+            const float g_o = my[9];
+            if (a.mip_filter != nullptr) {
+                my[10] = my[10] * act.e2.x / act.scale.x + g_o * act.opacity * act.f2 / (act.e2.x + act.f2);
+                my[11] = my[11] * act.e2.y / act.scale.y + g_o * act.opacity * act.f2 / (act.e2.y + act.f2);
+            } else {
+                my[10] *= act.scale.x;
+                my[11] *= act.scale.y;
+            }
+            my[9] = g_o * act.coef * act.sig * (1.0f - act.sig);
+            const float qg = quat.x * my[12] + quat.y * my[13] + quat.z * my[14] + quat.w * my[15];
+            my[12] = (my[12] - quat.x * qg) * act.inv_norm; my[13] = (my[13] - quat.y * qg) * act.inv_norm;
+            my[14] = (my[14] - quat.z * qg) * act.inv_norm; my[15] = (my[15] - quat.w * qg) * act.inv_norm;
         }
         // densification proxy (CR/backward.cu:637-640, quirk 5): depth = forward T[8]
         const float depth = q3.x;
@@ -527,34 +609,42 @@ __global__ void __launch_bounds__(PB_THREADS) project_bwd_kernel(ProjectBwdArgs 
     stream_out(a.dL_drots, 4, 12, a.accumulate & ACC_ROTATIONS);
     stream_out(a.dL_dtransMat, 9, 16, false);
     if (has_sh_out) {
-        const int row = M * 3;                            // 48 floats per Gaussian at M = 16
-        const int total = nvalid * row;
-        float* g = a.dL_dsh + (size_t)warp_base * row;
-        int i = lane / row, c = lane - i * row;
-        const bool acc_sh = a.accumulate & ACC_SH;
-        if (!acc_sh) {
-            for (int e = lane; e < total; e += 32) {      // every store instruction covers 128 contiguous bytes
-                g[e] = ((sh_rows >> i) & 1u) ? s_sh[warp][i * PB_SH_STRIDE + c] : 0.f;
-                c += 32;
-                while (c >= row) { c -= row; i++; }
+        // `row` floats per Gaussian taken from staging offset `src_off` of its SH row
+        auto write_sh = [&](float* dst, int row, int src_off) {
+            const int total = nvalid * row;
+            float* g = dst + (size_t)warp_base * row;
+            int i = lane / row, c = lane - i * row;
+            const bool acc_sh = a.accumulate & ACC_SH;
+            if (!acc_sh) {
+                for (int e = lane; e < total; e += 32) {      // every store instruction covers 128 contiguous bytes
+                    g[e] = ((sh_rows >> i) & 1u) ? s_sh[warp][i * PB_SH_STRIDE + src_off + c] : 0.f;
+                    c += 32;
+                    while (c >= row) { c -= row; i++; }
+                }
+            } else if ((row & 3) == 0 && src_off == 0) {
+                // running sum over views: only rows with a gradient are touched, 16 bytes per reduction
+                // (the row belongs to this warp alone; RED is used because it does not wait for the load)
+                const int quads = row >> 2;
+                const int nlive = __popc(sh_rows);
+                for (int f = lane; f < nlive * quads; f += 32) {
+                    const int k = f / quads, c4 = (f - k * quads) * 4;
+                    const int r = __fns(sh_rows, 0, k + 1);   // k-th row with a gradient
+                    const float* src = &s_sh[warp][r * PB_SH_STRIDE + c4];
+                    atomicAdd(reinterpret_cast<float4*>(g + (size_t)r * row + c4), make_float4(src[0], src[1], src[2], src[3]));
+                }
+            } else {
+                for (int e = lane; e < total; e += 32) {
+                    if ((sh_rows >> i) & 1u) atomicAdd(&g[e], s_sh[warp][i * PB_SH_STRIDE + src_off + c]);
+                    c += 32;
+                    while (c >= row) { c -= row; i++; }
+                }
             }
-        } else if ((row & 3) == 0) {
-            // running sum over views: only rows with a gradient are touched, 16 bytes per reduction
-            // (the row belongs to this warp alone; RED is used because it does not wait for the load)
-            const int quads = row >> 2;
-            const int nlive = __popc(sh_rows);
-            for (int f = lane; f < nlive * quads; f += 32) {
-                const int k = f / quads, c4 = (f - k * quads) * 4;
-                const int r = __fns(sh_rows, 0, k + 1);   // k-th row with a gradient
-                const float* src = &s_sh[warp][r * PB_SH_STRIDE + c4];
-                atomicAdd(reinterpret_cast<float4*>(g + (size_t)r * row + c4), make_float4(src[0], src[1], src[2], src[3]));
-            }
+        };
+        if (RAW) {   // the trainer's two SH tensors: _features_dc [P,1,3] and _features_rest [P,M-1,3]
+            write_sh(a.dL_dsh, 3, 0);
+            if (M > 1) write_sh(a.dL_dsh_rest, (M - 1) * 3, 3);
         } else {
-            for (int e = lane; e < total; e += 32) {
-                if ((sh_rows >> i) & 1u) atomicAdd(&g[e], s_sh[warp][i * PB_SH_STRIDE + c]);
-                c += 32;
-                while (c >= row) { c -= row; i++; }
-            }
+            write_sh(a.dL_dsh, M * 3, 0);
         }
     }
 }
@@ -594,7 +684,8 @@ void launch_densify_stats(int P, const float* dL_dmeans2D, const int* radii, flo
 }
 void launch_project_fwd(const ProjectArgs& a, cudaStream_t s) {
     if (a.P <= 0) return;
-    project_fwd_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a);
+    if (a.raw) project_fwd_kernel<true><<<(a.P + 255) / 256, 256, 0, s>>>(a);
+    else project_fwd_kernel<false><<<(a.P + 255) / 256, 256, 0, s>>>(a);
     count_launch();
 }
 void launch_scatter(const ScatterArgs& a, cudaStream_t s) {
@@ -604,7 +695,8 @@ void launch_scatter(const ScatterArgs& a, cudaStream_t s) {
 }
 void launch_project_bwd(const ProjectBwdArgs& a, cudaStream_t s) {
     if (a.P <= 0) return;
-    project_bwd_kernel<<<(a.P + PB_THREADS - 1) / PB_THREADS, PB_THREADS, 0, s>>>(a);
+    if (a.raw) project_bwd_kernel<true><<<(a.P + PB_THREADS - 1) / PB_THREADS, PB_THREADS, 0, s>>>(a);
+    else project_bwd_kernel<false><<<(a.P + PB_THREADS - 1) / PB_THREADS, PB_THREADS, 0, s>>>(a);
     count_launch();
 }
 void launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s) {

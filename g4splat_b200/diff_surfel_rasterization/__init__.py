@@ -148,6 +148,54 @@ def _sink_for(t: torch.Tensor):
     return _grad_sink.get((t.data_ptr(), tuple(t.shape)))
 
 
+def _plan_and_render(dev, P, W, H, bg, rs, plan):
+    """Forward of one view for P > 0: `plan(radii, geom, img, counts, stream_ptr)` issues g4s_forward_plan
+    (or its raw-parameter twin), then the render stage is launched speculatively (module docstring).
+    Returns (color, others, radii, geom, binning, img, capacity, num_rendered, pinned counts)."""
+    debug = bool(rs.debug)
+    f32 = dict(dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev)
+        sp = stream.cuda_stream
+        color = torch.empty((NUM_CHANNELS, H, W), **f32)
+        others = torch.empty((_OTHERS, H, W), **f32)
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
+        geom = torch.empty((_LIB.g4s_geom_bytes(P),), dtype=torch.uint8, device=dev)
+        img = torch.empty((_LIB.g4s_image_bytes(W, H),), dtype=torch.uint8, device=dev)
+        counts = _pinned_counts()
+        mode = _sync_mode()
+        if mode == "none":
+            _check_pending()
+        _lib.check(plan(radii, geom, img, counts, sp))
+        planned = torch.cuda.Event()
+        planned.record(stream)
+        cap = _capacity.guess(dev.index or 0, P)
+        while True:
+            binning = torch.empty((_LIB.g4s_binning_bytes(cap),), dtype=torch.uint8, device=dev)
+            if debug:
+                planned.synchronize()
+                if int(counts[0]) > cap:
+                    cap = int(counts[0])
+                    continue
+            _lib.check(_LIB.g4s_forward_render(
+                P, W, H, bg.data_ptr(), geom.data_ptr(), img.data_ptr(), binning.data_ptr(), cap,
+                color.data_ptr(), others.data_ptr(), sp, int(debug)))
+            if mode == "none":
+                _pending_overflow.append((planned, counts, cap))
+                num_rendered = -1
+                break
+            planned.synchronize()  # waits for project + scan only; the blend keeps running
+            num_rendered = int(counts[0])
+            last_counts.update(num_rendered=num_rendered, max_tile_list=int(counts[1]), visible=int(counts[2]))
+            _capacity.observe(dev.index or 0, num_rendered)
+            if num_rendered <= cap:
+                break
+            cap = _capacity.bucket(num_rendered + 65536)  # the speculative launch was a no-op: re-issue
+        if debug and rs.prefiltered and int(counts[3]) != 0:
+            raise RuntimeError("Point is filtered although prefiltered is set. This shouldn't happen!")
+    return color, others, radii, geom, binning, img, cap, num_rendered, counts
+
+
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
                         cov3Ds_precomp, raster_settings):
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales,
@@ -188,51 +236,15 @@ class _RasterizeGaussians(torch.autograd.Function):
             radii = torch.zeros((0,), dtype=torch.int32, device=dev)
             geom = binning = img = torch.empty((0,), dtype=torch.uint8, device=dev)
         else:
-            with torch.cuda.device(dev):
-                stream = torch.cuda.current_stream(dev)
-                sp = stream.cuda_stream
-                color = torch.empty((NUM_CHANNELS, H, W), **f32)
-                others = torch.empty((_OTHERS, H, W), **f32)
-                radii = torch.empty((P,), dtype=torch.int32, device=dev)
-                geom = torch.empty((_LIB.g4s_geom_bytes(P),), dtype=torch.uint8, device=dev)
-                img = torch.empty((_LIB.g4s_image_bytes(W, H),), dtype=torch.uint8, device=dev)
-                counts = _pinned_counts()
-                mode = _sync_mode()
-                if mode == "none":
-                    _check_pending()
-                _lib.check(_LIB.g4s_forward_plan(
+            def plan(radii, geom, img, counts, sp):
+                return _LIB.g4s_forward_plan(
                     P, int(rs.sh_degree), M, W, H, _ptr(means3D_c), _ptr(sh_c), _ptr(colors_c),
                     _ptr(opac_c), _ptr(scales_c), float(rs.scale_modifier), _ptr(rots_c), _ptr(cov_c),
                     _ptr(view), _ptr(proj), _ptr(campos), float(rs.tanfovx), float(rs.tanfovy),
                     int(bool(rs.prefiltered)), radii.data_ptr(), geom.data_ptr(), img.data_ptr(),
-                    counts.data_ptr(), sp, int(debug)))
-                planned = torch.cuda.Event()
-                planned.record(stream)
-                cap = _capacity.guess(dev.index or 0, P)
-                while True:
-                    binning = torch.empty((_LIB.g4s_binning_bytes(cap),), dtype=torch.uint8, device=dev)
-                    if debug:
-                        planned.synchronize()
-                        if int(counts[0]) > cap:
-                            cap = int(counts[0])
-                            continue
-                    _lib.check(_LIB.g4s_forward_render(
-                        P, W, H, bg.data_ptr(), geom.data_ptr(), img.data_ptr(), binning.data_ptr(), cap,
-                        color.data_ptr(), others.data_ptr(), sp, int(debug)))
-                    if mode == "none":
-                        _pending_overflow.append((planned, counts, cap))
-                        num_rendered = -1
-                        break
-                    planned.synchronize()  # waits for project + scan only; the blend keeps running
-                    num_rendered = int(counts[0])
-                    last_counts.update(num_rendered=num_rendered, max_tile_list=int(counts[1]), visible=int(counts[2]))
-                    _capacity.observe(dev.index or 0, num_rendered)
-                    if num_rendered <= cap:
-                        break
-                    cap = _capacity.bucket(num_rendered + 65536)  # the speculative launch was a no-op: re-issue
-                if debug and rs.prefiltered and int(counts[3]) != 0:
-                    raise RuntimeError("Point is filtered although prefiltered is set. This shouldn't happen!")
-                ctx.counts = counts
+                    counts.data_ptr(), sp, int(debug))
+            color, others, radii, geom, binning, img, cap, num_rendered, counts = _plan_and_render(dev, P, W, H, bg, rs, plan)
+            ctx.counts = counts
 
         ctx.sinks = {"means3D": _sink_for(means3D), "sh": _sink_for(sh), "opacities": _sink_for(opacities),
                      "scales": _sink_for(scales), "rotations": _sink_for(rotations)} if _grad_sink else None
@@ -298,6 +310,113 @@ class _RasterizeGaussians(torch.autograd.Function):
         # same order as the reference (RAST/diff_surfel_rasterization/__init__.py:144-154)
         return (dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales, dL_drotations,
                 dL_dtransMat, None)
+
+
+# ---- raw-parameter operator (extension) ----------------------------------------
+# The reference trainer activates its parameters with ~10 torch kernels (+ autograd) before every
+# operator call: exp / sqrt(s^2 + f^2), sigmoid (* mip compensation), normalize, cat(features_dc,
+# features_rest)  (2DGS/scene/gaussian_model.py:158-192).  `rasterize_gaussian_model` takes the
+# optimiser's leaves as they are stored and returns gradients with respect to them; the activations
+# run in registers inside the projection kernels (g4s_forward_plan_raw / g4s_backward_raw).
+def rasterize_gaussian_model(xyz, means2D, features_dc, features_rest, opacity, scaling, rotation, mip_filter,
+                             raster_settings):
+    """(color, radii, allmap) from un-activated parameters: xyz[P,3], features_dc[P,1,3],
+    features_rest[P,M-1,3], opacity[P,1], scaling[P,2], rotation[P,4] as GaussianModel stores them
+    (_xyz, _features_dc, _features_rest, _opacity, _scaling, _rotation) and mip_filter[P,1] or None
+    (use_mip_filter off).  Same outputs as GaussianRasterizer on the activated tensors."""
+    return _RasterizeGaussianModel.apply(xyz, means2D, features_dc, features_rest, opacity, scaling, rotation,
+                                         mip_filter, raster_settings)
+
+
+class _RasterizeGaussianModel(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz, means2D, features_dc, features_rest, opacity, scaling, rotation, mip_filter, raster_settings):
+        rs = raster_settings
+        if xyz.dim() != 2 or xyz.size(1) != 3:
+            raise RuntimeError("means3D must have dimensions (num_points, 3)")
+        dev = xyz.device
+        P = int(xyz.size(0))
+        H, W = int(rs.image_height), int(rs.image_width)
+        xyz_c = _f32c(xyz, "xyz")
+        dc_c = _f32c(features_dc, "features_dc")
+        rest_c = _f32c(features_rest, "features_rest")
+        opac_c = _f32c(opacity, "opacity")
+        scal_c = _f32c(scaling, "scaling")
+        rot_c = _f32c(rotation, "rotation")
+        mip_c = _f32c(mip_filter, "mip_filter") if mip_filter is not None else None
+        if P and (dc_c.shape != (P, 1, 3) or rest_c.dim() != 3 or rest_c.shape[0] != P or rest_c.shape[2] != 3 or
+                  opac_c.numel() != P or scal_c.shape != (P, 2) or rot_c.shape != (P, 4) or
+                  (mip_c is not None and mip_c.numel() != P)):
+            raise RuntimeError("rasterize_gaussian_model: parameter shapes do not match GaussianModel's "
+                               "(_features_dc [P,1,3], _features_rest [P,M-1,3], _opacity [P,1], _scaling [P,2], _rotation [P,4])")
+        M = 1 + int(rest_c.shape[1]) if P else 1
+        bg = _f32c(rs.bg, "background")
+        view = _f32c(rs.viewmatrix, "viewmatrix")
+        proj = _f32c(rs.projmatrix, "projmatrix")
+        campos = _f32c(rs.campos, "campos")
+        f32 = dict(dtype=torch.float32, device=dev)
+        num_rendered, cap = 0, 0
+        if P == 0:
+            color = torch.zeros((NUM_CHANNELS, H, W), **f32)
+            others = torch.zeros((_OTHERS, H, W), **f32)
+            radii = torch.zeros((0,), dtype=torch.int32, device=dev)
+            geom = binning = img = torch.empty((0,), dtype=torch.uint8, device=dev)
+        else:
+            def plan(radii, geom, img, counts, sp):
+                return _LIB.g4s_forward_plan_raw(
+                    P, int(rs.sh_degree), M, W, H, xyz_c.data_ptr(), dc_c.data_ptr(), _ptr(rest_c), opac_c.data_ptr(),
+                    scal_c.data_ptr(), float(rs.scale_modifier), rot_c.data_ptr(), _ptr(mip_c), _ptr(view), _ptr(proj),
+                    _ptr(campos), float(rs.tanfovx), float(rs.tanfovy), int(bool(rs.prefiltered)), radii.data_ptr(),
+                    geom.data_ptr(), img.data_ptr(), counts.data_ptr(), sp, int(bool(rs.debug)))
+            color, others, radii, geom, binning, img, cap, num_rendered, counts = _plan_and_render(dev, P, W, H, bg, rs, plan)
+            ctx.counts = counts
+        ctx.raster_settings = rs
+        ctx.num_rendered = num_rendered
+        ctx.M = M
+        ctx.capacity = cap
+        ctx.has_mip = mip_c is not None
+        ctx.save_for_backward(xyz_c, dc_c, rest_c, opac_c, scal_c, rot_c, mip_c if mip_c is not None else xyz_c.new_empty(0),
+                              radii, geom, binning, img)
+        ctx.mark_non_differentiable(radii)
+        return color, radii, others
+
+    @staticmethod
+    def backward(ctx, grad_out_color, grad_radii, grad_depth):
+        rs = ctx.raster_settings
+        xyz_c, dc_c, rest_c, opac_c, scal_c, rot_c, mip_c, radii, geom, binning, img = ctx.saved_tensors
+        dev = xyz_c.device
+        P, M = int(xyz_c.size(0)), ctx.M
+        H, W = int(rs.image_height), int(rs.image_width)
+        f32 = dict(dtype=torch.float32, device=dev)
+        alloc = torch.zeros if P == 0 else torch.empty  # every element is written by the kernels
+        # (the multi-view gradient sink of the operator API is not wired to the raw entry points: acc_mask = 0)
+        acc_mask = 0
+        g_xyz = k_xyz = alloc((P, 3), **f32)
+        g_dc = k_dc = alloc((P, 1, 3), **f32)
+        g_rest = k_rest = alloc((P, M - 1, 3), **f32)
+        g_op = k_op = alloc((P, 1), **f32)
+        g_sc = k_sc = alloc((P, 2), **f32)
+        g_rot = k_rot = alloc((P, 4), **f32)
+        g_means2D = alloc((P, 3), **f32)
+        if P != 0:
+            g_color = _f32c(grad_out_color, "dL_dout_color")
+            g_others = _f32c(grad_depth, "dL_dout_others")
+            bg = _f32c(rs.bg, "background")
+            view = _f32c(rs.viewmatrix, "viewmatrix")
+            proj = _f32c(rs.projmatrix, "projmatrix")
+            campos = _f32c(rs.campos, "campos")
+            with torch.cuda.device(dev):
+                sp = torch.cuda.current_stream(dev).cuda_stream
+                scratch = torch.empty((_LIB.g4s_backward_scratch_bytes_raw(P),), dtype=torch.uint8, device=dev)
+                _lib.check(_LIB.g4s_backward_raw(
+                    P, int(rs.sh_degree), M, W, H, bg.data_ptr(), xyz_c.data_ptr(), dc_c.data_ptr(), _ptr(rest_c),
+                    opac_c.data_ptr(), scal_c.data_ptr(), float(rs.scale_modifier), rot_c.data_ptr(),
+                    mip_c.data_ptr() if ctx.has_mip else None, _ptr(view), _ptr(proj), _ptr(campos),
+                    float(rs.tanfovx), float(rs.tanfovy), radii.data_ptr(), geom.data_ptr(), binning.data_ptr(),
+                    int(ctx.capacity), img.data_ptr(), g_color.data_ptr(), g_others.data_ptr(), k_xyz.data_ptr(),
+                    g_means2D.data_ptr(), k_dc.data_ptr(), _ptr(k_rest), k_op.data_ptr(), k_sc.data_ptr(),
+                    k_rot.data_ptr(), acc_mask, scratch.data_ptr(), sp, int(bool(rs.debug))))
+        return g_xyz, g_means2D, g_dc, g_rest, g_op, g_sc, g_rot, None, None
 
 
 def debug_pair_stats(rendered: torch.Tensor) -> dict:

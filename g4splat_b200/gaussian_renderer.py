@@ -12,7 +12,7 @@ import math
 
 import torch
 
-from .diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+from .diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer, rasterize_gaussian_model
 from .surface import surface_attributes
 
 
@@ -30,10 +30,16 @@ def _splat2pix_precomp(viewpoint_camera, pc, scaling_modifier):
     return (splat2world[:, [0, 1, 3]] @ world2pix[:, [0, 1, 3]]).permute(0, 2, 1).reshape(-1, 9)
 
 
-def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None):
+def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None,
+           fused_activations: bool = False):
     """Render the scene; bg_color must be on the GPU.  Same keys as the reference: render,
     viewspace_points, visibility_filter, radii, rend_alpha, rend_normal, rend_normal_cam, rend_dist,
-    surf_depth, surf_normal, surf_normal_cam, rend_depth."""
+    surf_depth, surf_normal, surf_normal_cam, rend_depth.
+
+    fused_activations (extension, off by default): read the model's raw leaves (_xyz, _features_dc,
+    _features_rest, _opacity, _scaling, _rotation, mip_filter) and let the projection kernels apply
+    get_scaling / get_rotation / get_opacity / get_features (scene/gaussian_model.py:158-192) in
+    registers; gradients arrive at the leaves directly."""
     xyz = pc.get_xyz
     # gradient carrier of the screen-space means (densification statistic), :27-31
     screenspace_points = torch.zeros_like(xyz, dtype=xyz.dtype, requires_grad=True, device=xyz.device) + 0
@@ -57,6 +63,17 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
         debug=False,
     )
     rasterizer = GaussianRasterizer(raster_settings=settings)
+
+    if fused_activations and override_color is None and not getattr(pipe, "compute_cov3D_python", False):
+        mip = pc.mip_filter if getattr(pc, "use_mip_filter", False) else None
+        rendered_image, radii, allmap = rasterize_gaussian_model(
+            pc._xyz, screenspace_points, pc._features_dc, pc._features_rest, pc._opacity, pc._scaling, pc._rotation,
+            mip, settings)
+        rets = {"render": rendered_image, "viewspace_points": screenspace_points,
+                "visibility_filter": radii > 0, "radii": radii}
+        rets.update(surface_attributes(allmap, viewpoint_camera.world_view_transform,
+                                       viewpoint_camera.full_proj_transform, pipe.depth_ratio))
+        return rets
 
     scales = rotations = cov3D_precomp = None
     if getattr(pipe, "compute_cov3D_python", False):

@@ -123,6 +123,39 @@ int g4s_backward(int P, int D, int M, int W, int H, const float* background,
                  float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dtransMat,
                  int accumulate_mask, void* scratch, void* stream, int debug);
 
+/* ---- raw-parameter entry points ---------------------------------------------
+ * The trainer calls the operator with ACTIVATED parameters: every render() runs exp / sigmoid /
+ * normalize / cat (and, with the mip filter, sqrt(s^2 + f^2) and the opacity compensation) as ~10
+ * torch kernels plus their autograd (2DGS/scene/gaussian_model.py:158-192 get_scaling, get_rotation,
+ * get_features, get_opacity; gaussian_renderer/__init__.py:55-106).  These two calls take the
+ * optimiser's own leaves instead, apply the activations in registers inside the projection kernels
+ * and return gradients with respect to the raw leaves:
+ *   xyz[P,3]  features_dc[P,1,3]  features_rest[P,M-1,3] (NULL when M == 1)  opacity_raw[P,1]
+ *   scaling_raw[P,2]  rotation_raw[P,4]  mip_filter[P] or NULL (use_mip_filter off)
+ * M counts all SH coefficients (1 + rest).  Everything else as in g4s_forward_plan / g4s_backward;
+ * g4s_forward_render is shared.  scratch for g4s_backward_raw: g4s_backward_scratch_bytes_raw(P). */
+size_t g4s_backward_scratch_bytes_raw(int P);
+int g4s_forward_plan_raw(int P, int D, int M, int W, int H,
+                         const float* xyz, const float* features_dc, const float* features_rest,
+                         const float* opacity_raw, const float* scaling_raw, float scale_modifier,
+                         const float* rotation_raw, const float* mip_filter,
+                         const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                         float tan_fovx, float tan_fovy, int prefiltered,
+                         int* radii, void* geom_buffer, void* img_buffer,
+                         int32_t* host_counts, void* stream, int debug);
+int g4s_backward_raw(int P, int D, int M, int W, int H, const float* background,
+                     const float* xyz, const float* features_dc, const float* features_rest,
+                     const float* opacity_raw, const float* scaling_raw, float scale_modifier,
+                     const float* rotation_raw, const float* mip_filter,
+                     const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                     float tan_fovx, float tan_fovy, const int* radii,
+                     const void* geom_buffer, const void* binning_buffer, int64_t capacity,
+                     const void* img_buffer,
+                     const float* dL_dout_color, const float* dL_dout_others,
+                     float* dL_dxyz, float* dL_dmeans2D, float* dL_dfeatures_dc, float* dL_dfeatures_rest,
+                     float* dL_dopacity_raw, float* dL_dscaling_raw, float* dL_drotation_raw,
+                     int accumulate_mask, void* scratch, void* stream, int debug);
+
 /* ---- markVisible --------------------------------------------------------------------------- */
 /* Replaces Rasterizer::markVisible / checkFrustum (rasterizer_impl.cu:54-66,141-153):
  * present[i] = (viewmatrix * means3D[i]).z > 0.2.  present is uint8[P] (bool). */

@@ -106,12 +106,50 @@ def bench_mip(iters):
                       "fraction_outside_2e-6": bad, "iters": iters}))
 
 
+def bench_activations(iters):
+    """One training-shaped view at c2 size: activate with the reference's torch operators and call the
+    operator, against the raw-parameter operator (activations inside the projection kernels)."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import helpers as Hh
+    import test_activations as TA
+    import g4splat_b200.diff_surfel_rasterization as op
+    from oracle import activations_oracle as AO
+    case = Hh.room_case("act_bench", P=1_000_000, W=1920, H=1080, seed=2, cams=64, cam_index=5)
+    raw_np, mip_np = TA.raw_from_case(case, True, seed=4)
+    raw = {k: torch.tensor(v, device="cuda", requires_grad=True) for k, v in raw_np.items()}
+    mip = torch.tensor(mip_np, device="cuda")
+    settings = Hh.make_settings(op, case, "cuda")
+    gc, go = (torch.tensor(a, device="cuda") for a in case.upstream())
+
+    def step(fused):
+        for v in raw.values():
+            v.grad = None
+        means2D = torch.zeros_like(raw["_xyz"], requires_grad=True)
+        if fused:
+            color, radii, allmap = op.rasterize_gaussian_model(raw["_xyz"], means2D, raw["_features_dc"], raw["_features_rest"],
+                                                               raw["_opacity"], raw["_scaling"], raw["_rotation"], mip, settings)
+        else:
+            act = AO.activate(raw, mip)
+            color, radii, allmap = op.GaussianRasterizer(raster_settings=settings)(
+                means3D=act["means3D"], means2D=means2D, opacities=act["opacities"], shs=act["shs"],
+                scales=act["scales"], rotations=act["rotations"])
+        torch.autograd.backward([color, allmap], [gc, go])
+
+    ms_f, ms_r = timed(lambda: step(True), iters), timed(lambda: step(False), iters)
+    print(json.dumps({"row": "one view forward + backward at c2 size (1.0 M surfels, 1920x1080, mip filter on), from raw leaves",
+                      "fused_ms": ms_f, "reference_torch_ops_ms": ms_r, "saved_ms_per_view": ms_r - ms_f,
+                      "speedup": ms_r / ms_f, "iters": iters,
+                      "note": "both arms use the B200 rasterizer; the difference is the activations (~10 torch kernels + autograd, "
+                              "incl. the 192 B/Gaussian cat of the SH tensors) against in-register activations"}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=30)
     args = ap.parse_args()
     bench_loss(args.iters)
     bench_mip(args.iters)
+    bench_activations(args.iters)
 
 
 if __name__ == "__main__":

@@ -76,7 +76,7 @@ def full(tag, out):
 
 
 STAGE_OF = {"project_fwd_kernel": "project_fwd", "tile_scan_kernel": "tile_scan", "scatter_kernel": "scatter",
-            "tile_sort_kernel": "tile_sort", "blend_fwd_kernel": "blend_fwd", "blend_fwd_tma_kernel": "blend_fwd",
+            "tile_sort_kernel": "tile_sort", "tile_sort_warp_kernel": "tile_sort", "blend_fwd_kernel": "blend_fwd", "blend_fwd_tma_kernel": "blend_fwd",
             "blend_bwd_kernel": "blend_bwd", "project_bwd_kernel": "project_bwd"}
 
 
@@ -93,7 +93,7 @@ def traffic(tag):
     mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     acc = {}
     for r in rows[2:]:
-        name = r[idx["Kernel Name"]].split("(")[0].split("::")[-1]
+        name = r[idx["Kernel Name"]].split("(")[0].split("<")[0].split("::")[-1]
         st = STAGE_OF.get(name)
         if st is None:
             continue
