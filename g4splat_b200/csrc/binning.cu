@@ -160,7 +160,7 @@ __device__ __forceinline__ void warp_bitonic_sort(unsigned long long (&key)[NREG
                 const bool lower = (lane & j) == 0;
 #pragma unroll
                 for (int r = 0; r < NREG; r++) {
-                    const bool asc = (k >= 64) ? (((r * 32) & k) == 0) : ((lane & k) == 0);
+                    const bool asc = (k >= 32) ? (((r * 32) & k) == 0) : ((lane & k) == 0);   // bit of k: register index or lane
                     const unsigned long long x = key[r];
                     const unsigned long long y = __shfl_xor_sync(0xffffffffu, x, j);
                     const bool want_min = (lower == asc);
