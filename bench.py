@@ -226,6 +226,86 @@ def run_steps(wl: Workload, mod, sync, steps: int, first_step: int, e2e: bool):
     return last
 
 
+# ------------------------------------------------------------- whole training iteration (8f rows)
+class RawModel:
+    """The optimiser's leaves as GaussianModel stores them (scene/gaussian_model.py:253-260), derived once
+    from the workload's activated parameters, and the properties render() reads.  The properties are the
+    reference's own torch expressions (gaussian_model.py:158-192)."""
+
+    def __init__(self, wl: "Workload"):
+        import torch
+        p = wl.params
+        with torch.no_grad():
+            op = p["opacity"].clamp(1e-4, 1 - 1e-4)
+            leaves = {"_xyz": p["xyz"].clone(), "_features_dc": p["features"][:, :1].contiguous(),
+                      "_features_rest": p["features"][:, 1:].contiguous(), "_opacity": torch.log(op / (1 - op)),
+                      "_scaling": torch.log(p["scaling"]), "_rotation": p["rotation"].clone()}
+        for k, v in leaves.items():
+            setattr(self, k, v.detach().requires_grad_(True))
+        self.active_sh_degree = self.max_sh_degree = 3
+        self.use_mip_filter = False
+
+    def leaves(self):
+        return [self._xyz, self._features_dc, self._features_rest, self._opacity, self._scaling, self._rotation]
+
+    get_xyz = property(lambda s: s._xyz)
+    get_scaling = property(lambda s: __import__("torch").exp(s._scaling))
+    get_rotation = property(lambda s: __import__("torch").nn.functional.normalize(s._rotation))
+    get_features = property(lambda s: __import__("torch").cat((s._features_dc, s._features_rest), dim=1))
+    get_opacity = property(lambda s: __import__("torch").sigmoid(s._opacity))
+
+
+def train_iteration(wl: "Workload", model: RawModel, mod, vid: int, gt, fused: bool):
+    """One view of train_with_refine_depth.py:378-399 from the raw leaves: activations -> rasterizer -> render()'s
+    post-processing -> 0.8 L1 + 0.2 D-SSIM + 0.05 normal consistency + 100 distortion -> backward.
+    fused=True: this repository's kernels for every row (rasterize_gaussian_model, surface_attributes,
+    photometric_loss); fused=False: the reference's torch operator sequences around `mod`'s rasterizer
+    (oracle/{surface,loss}_oracle.py restate gaussian_renderer/__init__.py:118-164 and utils/loss_utils.py)."""
+    import torch
+    c, cd = wl.cams[vid], wl.cam_dev[vid]
+    settings = wl.settings(mod, vid)
+    means2D = torch.zeros_like(model._xyz, requires_grad=True)
+    if fused:
+        from g4splat_b200.diff_surfel_rasterization import rasterize_gaussian_model
+        from g4splat_b200.surface import surface_attributes
+        from g4splat_b200.loss_utils import photometric_loss
+        color, radii, allmap = rasterize_gaussian_model(model._xyz, means2D, model._features_dc, model._features_rest,
+                                                        model._opacity, model._scaling, model._rotation, None, settings)
+        pkg = surface_attributes(allmap, cd["view"], cd["proj"], 0.0)
+        loss, _ = photometric_loss(color, gt, 0.2)
+    else:
+        from oracle import loss_oracle as LO
+        from oracle import surface_oracle as SO
+        rast = mod.GaussianRasterizer(raster_settings=settings)
+        color, radii, allmap = rast(means3D=model.get_xyz, means2D=means2D, opacities=model.get_opacity, shs=model.get_features,
+                                    scales=model.get_scaling, rotations=model.get_rotation)
+        pkg = SO.surface_attributes(allmap, cd["view"], cd["proj"], 0.0)
+        loss = 0.8 * LO.l1_loss(color, gt) + 0.2 * (1.0 - LO.ssim(color, gt))
+    normal_error = (1 - (pkg["rend_normal"] * pkg["surf_normal"]).sum(dim=0))[None]
+    total = loss + 0.05 * normal_error.mean() + 100.0 * pkg["rend_dist"].mean()
+    total.backward()
+    return total.detach()
+
+
+def time_train_iteration(wl: "Workload", mod, fused: bool, views: int, device):
+    """ms per view of `train_iteration` over `views` ring cameras (photograph resident on the device)."""
+    import torch
+    model = RawModel(wl)
+    gt = wl.gt_host[0].to(device).to(torch.float32) * (1.0 / 255.0)
+    for v in range(3):
+        train_iteration(wl, model, mod, v, gt, fused)
+    for leaf in model.leaves():
+        leaf.grad = None
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for v in range(views):
+        train_iteration(wl, model, mod, (3 + v) % CAM_RING, gt, fused)
+    e1.record()
+    torch.cuda.synchronize(device)
+    return e0.elapsed_time(e1) / views
+
+
 def time_region(fn, device, dist_on):
     import torch
     import torch.distributed as dist
@@ -275,6 +355,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--views", type=int, default=8, help="views per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-iteration", action="store_true", help="skip the informational whole-iteration timing")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -364,6 +445,19 @@ def main():
     h2d = args.views * (3 * N)          # one uint8 image per view
     d2h = 4                             # the scalar loss
 
+    train_it = None
+    if world == 1 and not args.no_train_iteration:
+        sync.zero()
+        if hasattr(mod, "set_gradient_sink"):
+            mod.set_gradient_sink(None)   # the multi-view gradient sink belongs to the step loops above
+        fused = args.impl != "reference"
+        ms_it = time_train_iteration(wl, mod, fused, 16, device)
+        train_it = {"ms_per_view": ms_it, "gaussians_per_s": P / (ms_it * 1e-3),
+                    "what": "one view of train_with_refine_depth.py:378-399 from the optimiser's raw leaves: activations, rasterizer, "
+                            "render() post-processing, 0.8 L1 + 0.2 D-SSIM + normal + distortion loss, backward (SURVEY.md 8f rows 1, 2, 4)",
+                    "arm": "this repository's fused kernels for every row" if fused else
+                           "the reference rasterizer with the reference's torch operator sequences around it"}
+
     pair_stats = None
     if lib is not None and rank == 0:
         import g4splat_b200.diff_surfel_rasterization as op_mod
@@ -394,6 +488,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clk}
+    if train_it is not None:
+        line["train_iteration"] = train_it
     if args.impl == "reference":
         line["impl"] = "reference"
         line["gpu_launches"] = None

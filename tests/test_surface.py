@@ -160,7 +160,7 @@ def test_kernels_full_size_against_fp64(b200, oracle32):
         for k in ALL:
             finite = np.isfinite(o64[k])
             assert np.isfinite(got[k]).all(), k
-            tol = 3e-4 if (k in loose and ratio < 1.0) else 2e-5
+            tol = (3e-4 if ratio < 1.0 else 5e-5) if k in loose else 2e-5   # fp32 differences of ~2.5 m depths at 1080p
             assert _rel(got[k], o64[k], finite) < tol, (ratio, k, _rel(got[k], o64[k], finite))
     torch.cuda.synchronize()
 
