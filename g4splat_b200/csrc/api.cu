@@ -97,9 +97,7 @@ size_t g4s_geom_bytes(int P) { return geom_layout(P, nullptr, nullptr); }
 size_t g4s_image_bytes(int W, int H) { return image_layout(W, H, nullptr, nullptr); }
 size_t g4s_binning_bytes(int64_t capacity) { return bin_layout(capacity, nullptr, nullptr); }
 size_t g4s_backward_scratch_bytes(int P) { return align_up((size_t)(P > 0 ? P : 1) * ACC_FLOATS * sizeof(float), 256); }
-size_t g4s_backward_scratch_bytes_raw(int P) {
-    return g4s_backward_scratch_bytes(P) + align_up((size_t)(P > 0 ? P : 1) * (3 + 9) * sizeof(float), 256);
-}
+size_t g4s_backward_scratch_bytes_raw(int P) { return g4s_backward_scratch_bytes(P); }
 
 }  // extern "C"
 
@@ -255,8 +253,8 @@ static int backward_impl(int P, int D, int M, int W, int H, const float* backgro
     if (P < 0 || W <= 0 || H <= 0 || capacity < 0) return fail(G4S_EINVAL, "g4s_backward: bad sizes");
     if (P == 0) return G4S_OK;
     if (!geom_buffer || !binning_buffer || !img_buffer || !scratch || !dL_dout_color || !dL_dout_others ||
-        !dL_dmeans3D || !dL_dmeans2D || !dL_dcolors || !dL_dopacity || !dL_dscales || !dL_drotations ||
-        !dL_dtransMat || !radii || !means3D || !background)
+        !dL_dmeans3D || !dL_dmeans2D || !dL_dopacity || !dL_dscales || !dL_drotations ||
+        !radii || !means3D || !background)
         return fail(G4S_EINVAL, "g4s_backward: null buffer");
     if (M > 0 && shs && !dL_dsh) return fail(G4S_EINVAL, "g4s_backward: dL_dsh required");
     if (M > 16) return fail(G4S_EINVAL, "g4s_backward: at most 16 SH coefficients (degree 3) are supported");
@@ -309,8 +307,10 @@ int g4s_backward(int P, int D, int M, int W, int H, const float* background, con
                  float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dtransMat,
                  int accumulate_mask, void* scratch, void* stream, int debug) {
     (void)scale_modifier; (void)colors_precomp; (void)transMat_precomp;
-    if (P > 0 && (!dL_dmeans3D || !dL_dmeans2D || !dL_dcolors || !dL_dopacity || !dL_dscales || !dL_drotations || !dL_dtransMat))
+    if (P > 0 && (!dL_dmeans3D || !dL_dmeans2D || !dL_dopacity || !dL_dscales || !dL_drotations))
         return fail(G4S_EINVAL, "g4s_backward: null buffer");
+    if (P > 0 && ((colors_precomp && !dL_dcolors) || (transMat_precomp && !dL_dtransMat)))
+        return fail(G4S_EINVAL, "g4s_backward: a precomputed input needs its gradient buffer");
     return backward_impl(P, D, M, W, H, background, means3D, shs, scales, rotations, viewmatrix, projmatrix, cam_pos,
                          tan_fovx, tan_fovy, radii, geom_buffer, binning_buffer, capacity, img_buffer, dL_dout_color,
                          dL_dout_others, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales,
@@ -330,13 +330,11 @@ int g4s_backward_raw(int P, int D, int M, int W, int H, const float* background,
     if (P > 0 && (!features_dc || !opacity_raw || !scaling_raw || !rotation_raw || !dL_dxyz || !dL_dmeans2D || !dL_dfeatures_dc ||
                   !dL_dopacity_raw || !dL_dscaling_raw || !dL_drotation_raw || (M > 1 && (!features_rest || !dL_dfeatures_rest))))
         return fail(G4S_EINVAL, "g4s_backward_raw: null buffer");
-    // the operator-only outputs (dL_dcolors_precomp, dL_dtransMat) have no raw counterpart: the tail of the
-    // scratch buffer takes them (g4s_backward_scratch_bytes_raw)
-    float* spill = P > 0 ? (float*)((char*)scratch + g4s_backward_scratch_bytes(P)) : nullptr;
+    // the operator-only outputs (dL_dcolors_precomp, dL_dtransMat) have no raw counterpart: not written
     return backward_impl(P, D, M, W, H, background, xyz, features_dc, scaling_raw, rotation_raw, viewmatrix, projmatrix, cam_pos,
                          tan_fovx, tan_fovy, radii, geom_buffer, binning_buffer, capacity, img_buffer, dL_dout_color,
-                         dL_dout_others, dL_dxyz, dL_dmeans2D, dL_dfeatures_dc, spill, dL_dopacity_raw, dL_dscaling_raw,
-                         dL_drotation_raw, spill ? spill + (size_t)3 * P : nullptr, accumulate_mask, scratch, stream, debug,
+                         dL_dout_others, dL_dxyz, dL_dmeans2D, dL_dfeatures_dc, nullptr, dL_dopacity_raw, dL_dscaling_raw,
+                         dL_drotation_raw, nullptr, accumulate_mask, scratch, stream, debug,
                          1, features_rest, opacity_raw, mip_filter, dL_dfeatures_rest);
 }
 

@@ -603,11 +603,11 @@ __global__ void __launch_bounds__(PB_THREADS) project_bwd_kernel(ProjectBwdArgs 
     };
     stream_out(a.dL_dmeans3D, 3, 0, a.accumulate & ACC_MEANS3D);
     stream_out(a.dL_dmeans2D, 3, 3, false);
-    stream_out(a.dL_dcolors, 3, 6, false);
+    if (a.dL_dcolors) stream_out(a.dL_dcolors, 3, 6, false);       // null: colours came from SH, nobody reads this
     stream_out(a.dL_dopacity, 1, 9, a.accumulate & ACC_OPACITY);
     stream_out(a.dL_dscales, 2, 10, a.accumulate & ACC_SCALES);
     stream_out(a.dL_drots, 4, 12, a.accumulate & ACC_ROTATIONS);
-    stream_out(a.dL_dtransMat, 9, 16, false);
+    if (a.dL_dtransMat) stream_out(a.dL_dtransMat, 9, 16, false);  // null: T came from scales / rotations
     if (has_sh_out) {
         // `row` floats per Gaussian taken from staging offset `src_off` of its SH row
         auto write_sh = [&](float* dst, int row, int src_off) {

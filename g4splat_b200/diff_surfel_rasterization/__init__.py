@@ -285,8 +285,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         k_scales, dL_dscales = out("scales", (P, 2))
         k_rots, dL_drotations = out("rotations", (P, 4))
         dL_dmeans2D = alloc((P, 3), **f32)
-        dL_dcolors = alloc((P, NUM_CHANNELS), **f32)
-        dL_dtransMat = alloc((P, 9), **f32)
+        # gradients of inputs that were not given (empty tensors) are never read by autograd: not computed
+        dL_dcolors = alloc((P, NUM_CHANNELS), **f32) if colors_c.numel() else None
+        dL_dtransMat = alloc((P, 9), **f32) if cov_c.numel() else None
         if P != 0:
             if M > 0 and sh_c.numel() == 0 and dL_dsh is not None:
                 dL_dsh.zero_()
@@ -304,9 +305,9 @@ class _RasterizeGaussians(torch.autograd.Function):
                     _ptr(scales_c), float(rs.scale_modifier), _ptr(rots_c), _ptr(cov_c), _ptr(view), _ptr(proj),
                     _ptr(campos), float(rs.tanfovx), float(rs.tanfovy), radii.data_ptr(), geom.data_ptr(),
                     binning.data_ptr(), int(ctx.capacity), img.data_ptr(), g_color.data_ptr(), g_others.data_ptr(),
-                    k_means3D.data_ptr(), dL_dmeans2D.data_ptr(), _ptr(k_sh), dL_dcolors.data_ptr(),
+                    k_means3D.data_ptr(), dL_dmeans2D.data_ptr(), _ptr(k_sh), _ptr(dL_dcolors),
                     k_opacity.data_ptr(), k_scales.data_ptr(), k_rots.data_ptr(),
-                    dL_dtransMat.data_ptr(), acc_mask, scratch.data_ptr(), sp, int(bool(rs.debug))))
+                    _ptr(dL_dtransMat), acc_mask, scratch.data_ptr(), sp, int(bool(rs.debug))))
         # same order as the reference (RAST/diff_surfel_rasterization/__init__.py:144-154)
         return (dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales, dL_drotations,
                 dL_dtransMat, None)

@@ -100,6 +100,8 @@ int g4s_forward_render(int P, int W, int H, const float* background,
  * element is written (zeros for Gaussians that were not visible), callers need not zero them.
  * Outputs (device): dL_dmeans3D[P,3] dL_dmeans2D[P,3] dL_dsh[P,M,3] (may be NULL when M == 0)
  *   dL_dcolors[P,3] dL_dopacity[P] dL_dscales[P,2] dL_drotations[P,4] dL_dtransMat[P,9].
+ *   dL_dcolors may be NULL when colors_precomp is NULL, dL_dtransMat when transMat_precomp is NULL
+ *   (the reference returns dense tensors autograd then drops; 48 B per Gaussian of writes saved).
  * scratch: g4s_backward_scratch_bytes(P) bytes.  capacity: the value g4s_forward_render was given
  * for this binning_buffer.
  * accumulate_mask (0 = reference behaviour): G4S_ACC_* bits select outputs that are running sums
