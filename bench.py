@@ -350,7 +350,7 @@ def cpu_oracle_step(cfg_name: str = CONFIG, threads: int = 0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--views", type=int, default=8, help="views per GPU per step")
@@ -417,12 +417,15 @@ def main():
 
     # ---- device-resident throughput ("value") -------------------------------------------------
     run_steps(wl, mod, sync, warmup, 0, e2e=False)
-    if lib is not None:
-        lib.g4s_profile_enable(1)
-    launches0 = lib.g4s_launch_count() if lib is not None else 0
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    # one more untimed step while nvidia-smi starts up (its NVML initialisation takes a driver lock for
+    # tens of milliseconds and would otherwise land inside the timed region)
+    run_steps(wl, mod, sync, 1, warmup - 1, e2e=False)
+    if lib is not None:
+        lib.g4s_profile_enable(1)
+    launches0 = lib.g4s_launch_count() if lib is not None else 0
     ms, _ = time_region(lambda: run_steps(wl, mod, sync, args.steps, warmup, e2e=False), device, dist_on)
     clk = clocks.stop() if rank == 0 else None
     launches = (lib.g4s_launch_count() - launches0) if lib is not None else None

@@ -93,7 +93,7 @@ def traffic(tag):
     mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     acc = {}
     for r in rows[2:]:
-        name = r[idx["Kernel Name"]].split("(")[0].split("<")[0].split("::")[-1]
+        name = r[idx["Kernel Name"]].split("(")[0].split("<")[0].split("::")[-1].split()[-1]
         st = STAGE_OF.get(name)
         if st is None:
             continue
