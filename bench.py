@@ -57,35 +57,90 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    """SM clock and throttle reasons sampled every 100 ms while the timed region runs.
+
+    Source: the NVML calls behind `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*`
+    made from a thread of this process (nvidia_ml_py); G4S_BENCH_CLOCKS=smi spawns nvidia-smi itself
+    (`-lms 200`, the profiling recipe's line), =off disables sampling.  In-process NVML is the default
+    because a polling nvidia-smi process that lands on the core of the launching thread stretches the
+    (host-synchronised) step loop by tens of percent in some runs (profiles/r01t_bench_stability.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
+        self.mode = os.environ.get("G4S_BENCH_CLOCKS", "nvml")
         self.proc = None
         self.lines = []
+        self.samples = []      # (sm_mhz, max_mhz, reason bits)
+        self._stop = threading.Event()
+        self._thread = None
+
+    # physical index of the visible device `idx` (CUDA_VISIBLE_DEVICES may renumber)
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.idx < len(ids) and ids[self.idx].isdigit():
+                return int(ids[self.idx])
+        return self.idx
 
     def start(self):
+        if self.mode == "off":
+            return
+        if self.mode == "nvml":
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                self._h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+                self._nv = pynvml
+                self._thread = threading.Thread(target=self._poll_nvml, daemon=True)
+                self._thread.start()
+                return
+            except Exception:  # noqa: BLE001
+                self.mode = "smi"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "200", "-i", str(self._physical_index())], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:  # noqa: BLE001
             self.proc = None
+
+    def _poll_nvml(self):
+        nv = self._nv
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                self.samples.append((float(sm), float(mx), {n for n, b in bits.items() if r & b}))
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.1)
 
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.mode == "off":
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampling disabled (G4S_BENCH_CLOCKS=off)"]}
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=1.0)
+            sm = [s[0] for s in self.samples]
+            reasons = set().union(*[s[2] for s in self.samples]) if self.samples else set()
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(s[1] for s in self.samples) if sm else None,
+                    "reasons": sorted(reasons), "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.25)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
@@ -94,11 +149,11 @@ class ClockSampler:
                 sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[4:8]):
+            for n, v in zip(self.NAMES, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def algorithmic_bytes(stage: str, P: int, V: int, R: int, N: int, T: int, K: int, M: int) -> float:
