@@ -252,12 +252,20 @@ class Workload:
         return color, radii, allmap, means2D
 
 
+STEP_TRACE = []   # G4S_BENCH_TRACE=1: a CUDA event after every step (diagnostics; read after the timed region)
+
+
 def run_steps(wl: Workload, mod, sync, steps: int, first_step: int, e2e: bool):
     """`steps` optimisation-step-shaped passes; returns the last loss value (e2e) or None."""
     import torch
     last = None
+    trace = os.environ.get("G4S_BENCH_TRACE") == "1"
     slot = wl.prefetch_image(first_step) if e2e else None
     for s in range(first_step, first_step + steps):
+        if trace:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            STEP_TRACE.append((s, e2e, ev, op_counts_snapshot(mod)))
         loss_acc = None
         for k, vid in enumerate(wl.view_ids(s)):
             if e2e:
@@ -359,6 +367,20 @@ def time_train_iteration(wl: "Workload", mod, fused: bool, views: int, device):
     e1.record()
     torch.cuda.synchronize(device)
     return e0.elapsed_time(e1) / views
+
+
+def op_counts_snapshot(mod):
+    lc = getattr(mod, "last_counts", None)
+    return dict(lc) if lc else None
+
+
+def dump_trace():
+    if not STEP_TRACE:
+        return
+    rows = []
+    for (s0, e0, ev0, c0), (s1, e1, ev1, c1) in zip(STEP_TRACE[:-1], STEP_TRACE[1:]):
+        rows.append(f"step {s0:5d} {'e2e' if e0 else 'dev'} {ev0.elapsed_time(ev1):7.2f} ms  {c1}")
+    sys.stderr.write("\n".join(rows) + "\n")
 
 
 def time_region(fn, device, dist_on):
@@ -598,6 +620,7 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"1 view forward+backward at full c2 size, {dt:.1f} s"}
     print(json.dumps(line))
+    dump_trace()
     if dist_on:
         dist.destroy_process_group()
     return 0

@@ -37,27 +37,35 @@ enum { ST_PROJECT_FWD = 0, ST_TILE_SCAN, ST_SCATTER, ST_TILE_SORT, ST_BLEND_FWD,
 static const char* const kStageNames[ST_COUNT] = {"project_fwd", "tile_scan", "scatter", "tile_sort", "blend_fwd",
                                                   "acc_clear", "blend_bwd", "project_bwd"};
 static bool g_profile = false;
-static cudaEvent_t g_ev_begin[ST_COUNT], g_ev_end[ST_COUNT];
-static bool g_ev_valid[ST_COUNT] = {false};
+// A small ring of event pairs per stage: a slot is folded into the running mean when it comes up
+// for reuse, RING launches later, by which time it has completed even when the host runs ahead of
+// the device by a whole view.
+constexpr int EV_RING = 4;
+static cudaEvent_t g_ev_begin[ST_COUNT][EV_RING], g_ev_end[ST_COUNT][EV_RING];
+static bool g_ev_valid[ST_COUNT][EV_RING] = {{false}};
+static unsigned g_ev_next[ST_COUNT] = {0};
 static bool g_ev_created = false;
 static double g_ev_sum_ms[ST_COUNT] = {0};
 static long long g_ev_n[ST_COUNT] = {0};
-// fold the previous launch of `stage` into the running mean if its events have completed
-static void harvest(int stage, bool wait) {
-    if (!g_ev_valid[stage]) return;
-    if (wait) { if (cudaEventSynchronize(g_ev_end[stage]) != cudaSuccess) return; }
-    else if (cudaEventQuery(g_ev_end[stage]) != cudaSuccess) { cudaGetLastError(); g_ev_valid[stage] = false; return; }
+static void harvest(int stage, int slot, bool wait) {
+    if (!g_ev_valid[stage][slot]) return;
+    if (wait) { if (cudaEventSynchronize(g_ev_end[stage][slot]) != cudaSuccess) return; }
+    else if (cudaEventQuery(g_ev_end[stage][slot]) != cudaSuccess) { cudaGetLastError(); g_ev_valid[stage][slot] = false; return; }
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, g_ev_begin[stage], g_ev_end[stage]) == cudaSuccess) { g_ev_sum_ms[stage] += ms; g_ev_n[stage]++; }
-    g_ev_valid[stage] = false;
+    if (cudaEventElapsedTime(&ms, g_ev_begin[stage][slot], g_ev_end[stage][slot]) == cudaSuccess) { g_ev_sum_ms[stage] += ms; g_ev_n[stage]++; }
+    g_ev_valid[stage][slot] = false;
 }
 struct StageTimer {
-    int stage; cudaStream_t s;
-    StageTimer(int st, cudaStream_t stream) : stage(st), s(stream) {
-        if (g_profile) { harvest(stage, false); cudaEventRecord(g_ev_begin[stage], s); }
+    int stage, slot; cudaStream_t s;
+    StageTimer(int st, cudaStream_t stream) : stage(st), slot(0), s(stream) {
+        if (g_profile) {
+            slot = (int)(g_ev_next[stage]++ % EV_RING);
+            harvest(stage, slot, false);
+            cudaEventRecord(g_ev_begin[stage][slot], s);
+        }
     }
     ~StageTimer() {
-        if (g_profile) { cudaEventRecord(g_ev_end[stage], s); g_ev_valid[stage] = true; }
+        if (g_profile) { cudaEventRecord(g_ev_end[stage][slot], s); g_ev_valid[stage][slot] = true; }
     }
 };
 }  // namespace g4s
@@ -68,21 +76,24 @@ extern "C" {
 
 int g4s_profile_enable(int on) {
     if (on && !g_ev_created) {
-        for (int i = 0; i < ST_COUNT; i++) {
-            if (cudaEventCreate(&g_ev_begin[i]) != cudaSuccess || cudaEventCreate(&g_ev_end[i]) != cudaSuccess)
-                return fail(G4S_ECUDA, "g4s_profile_enable: cudaEventCreate failed");
-        }
+        for (int i = 0; i < ST_COUNT; i++)
+            for (int k = 0; k < EV_RING; k++)
+                if (cudaEventCreate(&g_ev_begin[i][k]) != cudaSuccess || cudaEventCreate(&g_ev_end[i][k]) != cudaSuccess)
+                    return fail(G4S_ECUDA, "g4s_profile_enable: cudaEventCreate failed");
         g_ev_created = true;
     }
     g_profile = on != 0;
-    for (int i = 0; i < ST_COUNT; i++) { g_ev_valid[i] = false; g_ev_sum_ms[i] = 0; g_ev_n[i] = 0; }
+    for (int i = 0; i < ST_COUNT; i++) {
+        for (int k = 0; k < EV_RING; k++) g_ev_valid[i][k] = false;
+        g_ev_sum_ms[i] = 0; g_ev_n[i] = 0; g_ev_next[i] = 0;
+    }
     return G4S_OK;
 }
 int g4s_profile_num_stages(void) { return ST_COUNT; }
 const char* g4s_profile_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : ""; }
 int g4s_profile_read(float* mean_ms_out, int64_t* count_out, int n) {
     for (int i = 0; i < n && i < ST_COUNT; i++) {
-        harvest(i, true);
+        for (int k = 0; k < EV_RING; k++) harvest(i, k, true);
         mean_ms_out[i] = g_ev_n[i] ? (float)(g_ev_sum_ms[i] / (double)g_ev_n[i]) : -1.0f;
         if (count_out) count_out[i] = g_ev_n[i];
     }
