@@ -384,8 +384,13 @@ def dump_trace():
 
 
 def time_region(fn, device, dist_on):
+    import gc
     import torch
     import torch.distributed as dist
+    # no cyclic-GC pause inside the timed region (the step loop is host-synchronised once per view, so a
+    # 50 ms generation-2 collection shows up one to one); reference counting still frees every tensor
+    gc.collect()
+    gc.disable()
     if dist_on:
         dist.barrier()
     torch.cuda.synchronize(device)
@@ -394,6 +399,7 @@ def time_region(fn, device, dist_on):
     out = fn()
     e1.record()
     torch.cuda.synchronize(device)
+    gc.enable()
     ms = e0.elapsed_time(e1)
     if dist_on:
         t = torch.tensor([ms], device=device)
