@@ -77,7 +77,7 @@ def full(tag, out):
 
 STAGE_OF = {"project_fwd_kernel": "project_fwd", "tile_scan_kernel": "tile_scan", "scatter_kernel": "scatter",
             "tile_sort_kernel": "tile_sort", "tile_sort_warp_kernel": "tile_sort", "blend_fwd_kernel": "blend_fwd", "blend_fwd_tma_kernel": "blend_fwd",
-            "blend_bwd_kernel": "blend_bwd", "project_bwd_kernel": "project_bwd"}
+            "blend_bwd_kernel": "blend_bwd", "blend_fwd_warp_kernel": "blend_fwd", "blend_bwd_warp_kernel": "blend_bwd", "project_bwd_kernel": "project_bwd"}
 
 
 def traffic(tag):
