@@ -84,6 +84,15 @@ class _CapacityPolicy:
 
 
 _capacity = _CapacityPolicy()
+# G4S_HOST_TRACE=1: wall-clock of the host-side segments of every call (diagnostics; host_trace_summary())
+_HOST_TRACE = os.environ.get("G4S_HOST_TRACE") == "1"
+_host_times = {"fwd_launch": [], "fwd_wait": [], "bwd": []}
+
+
+def host_trace_summary() -> dict:
+    import statistics
+    return {k: dict(n=len(v), mean_us=1e6 * statistics.fmean(v), p50_us=1e6 * statistics.median(v), max_us=1e6 * max(v))
+            for k, v in _host_times.items() if v}
 # (num_rendered, longest tile list, visible Gaussians) of the most recent forward whose plan the
 # host has waited for; benchmarks read it to size the algorithmic-bytes model
 last_counts = {"num_rendered": 0, "max_tile_list": 0, "visible": 0}
@@ -154,6 +163,9 @@ def _plan_and_render(dev, P, W, H, bg, rs, plan):
     Returns (color, others, radii, geom, binning, img, capacity, num_rendered, pinned counts)."""
     debug = bool(rs.debug)
     f32 = dict(dtype=torch.float32, device=dev)
+    if _HOST_TRACE:
+        import time
+        t_begin = time.perf_counter()
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev)
         sp = stream.cuda_stream
@@ -184,7 +196,13 @@ def _plan_and_render(dev, P, W, H, bg, rs, plan):
                 _pending_overflow.append((planned, counts, cap))
                 num_rendered = -1
                 break
+            if _HOST_TRACE:
+                t_wait = time.perf_counter()
             planned.synchronize()  # waits for project + scan only; the blend keeps running
+            if _HOST_TRACE:
+                t_done = time.perf_counter()
+                _host_times["fwd_launch"].append(t_wait - t_begin)
+                _host_times["fwd_wait"].append(t_done - t_wait)
             num_rendered = int(counts[0])
             last_counts.update(num_rendered=num_rendered, max_tile_list=int(counts[1]), visible=int(counts[2]))
             _capacity.observe(dev.index or 0, num_rendered)
@@ -258,6 +276,9 @@ class _RasterizeGaussians(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out_color, grad_radii, grad_depth):
+        if _HOST_TRACE:
+            import time
+            t_begin = time.perf_counter()
         rs = ctx.raster_settings
         colors_c, means3D_c, scales_c, rots_c, cov_c, radii, sh_c, geom, binning, img = ctx.saved_tensors
         dev = means3D_c.device
@@ -308,6 +329,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                     k_means3D.data_ptr(), dL_dmeans2D.data_ptr(), _ptr(k_sh), _ptr(dL_dcolors),
                     k_opacity.data_ptr(), k_scales.data_ptr(), k_rots.data_ptr(),
                     _ptr(dL_dtransMat), acc_mask, scratch.data_ptr(), sp, int(bool(rs.debug))))
+        if _HOST_TRACE:
+            _host_times["bwd"].append(time.perf_counter() - t_begin)
         # same order as the reference (RAST/diff_surfel_rasterization/__init__.py:144-154)
         return (dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales, dL_drotations,
                 dL_dtransMat, None)
