@@ -166,7 +166,7 @@ def algorithmic_bytes(stage: str, P: int, V: int, R: int, N: int, T: int, K: int
         "scatter": V * 16 + R * (8 + 4),
         "tile_sort": R * (8 + 4) + T * 8,
         "blend_fwd": R * (4 + 112 + 32) + N * 60 + T * 12,      # list + record gather + contribution masks
-        "acc_clear": P * 80,
+        "acc_clear": P * 4 + V * 80,
         "blend_bwd": R * (4 + 96 + 32 + 80) + N * 60 + T * 12,  # + masks read + accumulator flush
         "project_bwd": P * (4 + 12 + 12 + 4 + 8 + 16 + 36 + 12 + 12 * M) + V * (80 + 96 + 40 + 12 * K),
     }[stage]

@@ -280,8 +280,9 @@ static int backward_impl(int P, int D, int M, int W, int H, const float* backgro
     float4* acc = (float4*)scratch;
     {
         StageTimer tm(ST_ACC_CLEAR, s);
-        if ((rc = check_cuda(cudaMemsetAsync(acc, 0, (size_t)P * ACC_FLOATS * sizeof(float), s), "memset acc"))) return rc;
+        launch_acc_clear(P, radii, acc, s);
     }
+    if ((rc = stage_check(debug, s, "acc_clear"))) return rc;
 
     BlendBwdArgs bb;
     bb.W = W; bb.H = H; bb.grid_x = gx; bb.grid_y = gy;

@@ -100,6 +100,7 @@ struct ProjectBwdArgs {
     float* dL_dscales; float* dL_drots; float* dL_dtransMat;
 };
 void launch_project_bwd(const ProjectBwdArgs& a, cudaStream_t s);
+void launch_acc_clear(int P, const int* radii, float4* acc, cudaStream_t s);
 
 void launch_densify_stats(int P, const float* dL_dmeans2D, const int* radii, float* accum, float* denom,
                           int* max_radii, cudaStream_t s);

@@ -675,6 +675,22 @@ __global__ void __launch_bounds__(256) densify_stats_kernel(int P, const float* 
     }
 }
 
+// Zero the blend-stage accumulator rows of the visible Gaussians only (the others are never read):
+// 4 B read per Gaussian + 80 B written per visible one, instead of an 80 P byte memset.
+__global__ void __launch_bounds__(256) acc_clear_kernel(int P, const int* __restrict__ radii, float4* __restrict__ acc) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P || radii[idx] <= 0) return;
+    float4* row = acc + (size_t)idx * ACC_F4;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < ACC_F4; q++) row[q] = z;
+}
+void launch_acc_clear(int P, const int* radii, float4* acc, cudaStream_t s) {
+    if (P <= 0) return;
+    acc_clear_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, radii, acc);
+    count_launch();
+}
+
 // ---- launchers --------------------------------------------------------------------------------
 void launch_densify_stats(int P, const float* dL_dmeans2D, const int* radii, float* accum, float* denom,
                           int* max_radii, cudaStream_t s) {
