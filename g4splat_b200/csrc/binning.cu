@@ -130,12 +130,12 @@ __device__ __forceinline__ void bitonic_sort_ascending(KeyArray keys, int n) {
     }
 }
 
-// Lists of up to WARP_SORT_MAX = 512 entries (nearly all of them: the mean list holds ~160) are sorted by ONE
+// Lists of up to WARP_SORT_MAX = 256 entries (nearly all of them: the mean list holds ~160) are sorted by ONE
 // warp in registers: element e = r * 32 + lane lives in register r of its lane, compare-exchange
 // partners at distance < 32 are reached with a shuffle, larger distances are other registers of the
 // same lane.  No shared memory, no block barrier; eight tiles per CTA.  Padding keys are all-ones
 // (greater than any depth<<32|index key), so they stay behind the n real entries.
-constexpr int WARP_SORT_MAX = 512;
+constexpr int WARP_SORT_MAX = 256;   // (512 with 16 registers per lane was measured: the long lists then form a single-warp tail, 0.063 -> 0.078 ms)
 
 template <int NREG>
 __device__ __forceinline__ void warp_bitonic_sort(unsigned long long (&key)[NREG], int lane) {
@@ -202,8 +202,7 @@ __global__ void __launch_bounds__(SORT_THREADS) tile_sort_warp_kernel(TileSortAr
     if (n <= 32) warp_sort_tile<1>(gk, out, n, lane);
     else if (n <= 64) warp_sort_tile<2>(gk, out, n, lane);
     else if (n <= 128) warp_sort_tile<4>(gk, out, n, lane);
-    else if (n <= 256) warp_sort_tile<8>(gk, out, n, lane);
-    else warp_sort_tile<16>(gk, out, n, lane);
+    else warp_sort_tile<8>(gk, out, n, lane);
 }
 
 // Lists longer than WARP_SORT_MAX: one CTA per tile, in shared memory.
