@@ -482,6 +482,7 @@ def main():
     dist_on = world > 1
     if dist_on:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=device)
 
     from g4splat_b200 import _lib
