@@ -135,3 +135,56 @@ def test_synthetic_scene_is_seeded_and_well_formed():
     R = cam.viewmatrix.T[:3, :3]
     assert np.allclose(R @ R.T, np.eye(3), atol=1e-5)
     assert np.allclose(cam.viewmatrix.T @ np.append(cam.campos, 1.0), [0, 0, 0, 1], atol=1e-4)
+
+
+# ---- caller-side mirrors: argument handling that needs no GPU ----------------------
+def test_caller_side_mirrors_reject_cpu_tensors_and_bad_shapes():
+    import g4splat_b200.diff_surfel_rasterization as op
+    from g4splat_b200.gaussian_model import compute_mip_filter
+    from g4splat_b200.loss_utils import photometric_loss, ssim
+    from g4splat_b200.surface import surface_attributes
+    img = torch.rand(3, 24, 32)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        photometric_loss(img, img, 0.2)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ssim(img, img)
+    with pytest.raises(NotImplementedError):
+        ssim(img, img, window_size=7)          # checked before the device: the reference's only configuration is 11
+    with pytest.raises(ValueError, match=r"\(C, H, W\)"):
+        photometric_loss(torch.rand(24, 32), torch.rand(24, 32), 0.2)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        surface_attributes(torch.rand(7, 8, 8), torch.eye(4), torch.eye(4), 1.0)
+    with pytest.raises(ValueError, match="7, H, W"):
+        surface_attributes(torch.rand(6, 8, 8), torch.eye(4), torch.eye(4), 1.0)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        compute_mip_filter(torch.zeros(4, 3), [])
+    rs = op.GaussianRasterizationSettings(16, 16, 1.0, 1.0, torch.zeros(3), 1.0, torch.eye(4), torch.eye(4), 3,
+                                          torch.zeros(3), False, False)
+    x = torch.zeros(4, 3)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        op.rasterize_gaussian_model(x, x, torch.zeros(4, 1, 3), torch.zeros(4, 15, 3), torch.zeros(4, 1),
+                                    torch.zeros(4, 2), torch.zeros(4, 4), None, rs)
+
+
+def test_mip_filter_camera_records_round_python_scalars_once():
+    """The reference multiplies Python floats (double) and lets torch round the result to fp32 once
+    (gaussian_model.py:416-420); the host builds the camera records the same way."""
+    import types
+    from g4splat_b200.gaussian_model import CAMERA_RECORD_FLOATS, camera_records
+    cam = types.SimpleNamespace(R=np.eye(3), T=np.array([0.1, 0.2, 0.3]), focal_x=1111.111111, focal_y=999.9,
+                                image_width=1237, image_height=821)
+    rec = camera_records([cam, cam])
+    assert rec.shape == (2, CAMERA_RECORD_FLOATS) and rec.dtype == np.float32
+    assert rec[0, 12] == np.float32(1111.111111) and rec[0, 14] == np.float32(1237 / 2.0)
+    assert rec[0, 16] == np.float32(-0.15 * 1237) and rec[0, 17] == np.float32(1237 * 1.15)
+    assert rec[0, 18] == np.float32(-0.15 * 821) and rec[0, 19] == np.float32(1.15 * 821)
+    assert np.array_equal(rec[0, 9:12], np.float32([0.1, 0.2, 0.3]))
+
+
+def test_loss_window_is_the_reference_gaussian():
+    from math import exp
+    from g4splat_b200 import loss_utils as LU
+    ref = torch.Tensor([exp(-(x - 5) ** 2 / float(2 * 1.5 ** 2)) for x in range(11)])
+    ref = ref / ref.sum()
+    assert torch.equal(LU.gaussian(), ref) and len(LU._WINDOW_C) == 11
+    assert all(float(LU._WINDOW_C[i]) == float(ref[i]) for i in range(11))
