@@ -198,6 +198,9 @@ class Workload:
         self.bg = torch.zeros(3, device=device)
         gc, go = S.make_upstream_grads(self.W, self.H, cfg["seed"])
         self.g_color, self.g_allmap = d(gc), d(go)
+        # e2e regulariser weights per allmap channel (depth, alpha, normal xyz, median depth, distortion), / pixels
+        n_pix = float(self.W * self.H)
+        self.reg_weights = torch.tensor([0.01, 0.0025, 0.0025, 0.0025, 0.0025, 0.01, 0.05], device=device).view(7, 1, 1) / n_pix
         # e2e: 8 distinct pinned uint8 "photographs" (random content; the loss only needs the bytes to move)
         rng = np.random.default_rng(123 + rank)
         self.gt_host = [torch.from_numpy(rng.integers(0, 256, size=(3, self.H, self.W), dtype=np.uint8)).pin_memory()
@@ -272,11 +275,13 @@ def run_steps(wl: Workload, mod, sync, steps: int, first_step: int, e2e: bool):
                 nxt = wl.prefetch_image(s + k + 1)           # next view's photograph: PCIe copy overlaps this view
             color, radii, allmap, means2D = wl.rasterize(mod, vid)
             if e2e:
-                gt = wl.image(slot).to(torch.float32) * (1.0 / 255.0)
+                gt = torch.mul(wl.image(slot), 1.0 / 255.0)      # uint8 -> float32 in one kernel
                 wl.release_image(slot)
                 slot = nxt
-                loss = (color - gt).abs().mean() + 0.05 * allmap[6].mean() + 0.01 * (allmap[0] + allmap[5]).mean() \
-                    + 0.01 * allmap[1:5].mean()
+                # L1 photometric term + regularisers on the seven allmap channels:
+                #   mean|color - gt| + 0.05 mean(distortion) + 0.01 mean(depth + median depth) + 0.01 mean(alpha, normal)
+                # written as one weighted sum so that both arms spend few launches on it
+                loss = torch.nn.functional.l1_loss(color, gt) + (allmap * wl.reg_weights).sum()
                 loss.backward()
                 loss_acc = loss.detach() if loss_acc is None else loss_acc + loss.detach()
             else:
