@@ -142,3 +142,34 @@ def test_raw_operator_full_size_and_render_option(oracle32):
     assert Hh.radii_mismatch(res[True]["radii"], res[False]["radii"], loose=True) <= 4
     Hh.assert_parity(res[True], res[False], tuple("d" + k for k in MG.RAW_KEYS), rtol=1e-3, max_bad_frac=2e-4,
                      what="render raw gradients")
+
+
+def _truncate_sh(case, M, degree):
+    """The same scene with only M allocated SH coefficients (a model trained with max_sh_degree < 3)."""
+    import copy
+    c = copy.copy(case)
+    c.scene = dict(case.scene)
+    c.scene["shs"] = np.ascontiguousarray(case.scene["shs"][:, :M])
+    c.sh_degree = degree
+    return c
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,degree", [(4, 1), (1, 0), (9, 2)])
+def test_fewer_allocated_sh_coefficients(M, degree, b200, oracle32):
+    """shs [P,M,3] with M < 16 (reference: M = sh.size(1), rasterize_points.cu:101-105): the operator against
+    the CPU oracle, and the raw-parameter operator (features_rest [P,M-1,3], empty for M = 1) against it."""
+    case = _truncate_sh(Hh.named_case("tiny", oracle32), M, degree)
+    want = Hh.run_oracle(oracle32, case)
+    got = Hh.run_operator(b200, case)
+    assert got["dL_dsh"].shape == (case.P, M, 3)
+    Hh.assert_parity(got, want, ("color", "allmap"), rtol=1e-4, max_bad_frac=2e-4, what=f"M={M} forward vs oracle")
+    Hh.assert_parity(got, want, Hh.GRAD_KEYS, rtol=1e-3, max_bad_frac=2e-4, what=f"M={M} backward vs oracle")
+    raw, _ = raw_from_case(case, False, seed=5)
+    assert raw["_features_rest"].shape == (case.P, M - 1, 3)
+    fused = _run(case, raw, None, fused=True)
+    Hh.assert_parity(fused, got, ("color", "allmap"), rtol=1e-4, max_bad_frac=2e-4, what=f"M={M} raw forward")
+    assert fused["d_features_rest"].shape == (case.P, M - 1, 3)
+    np.testing.assert_allclose(fused["d_features_dc"][:, 0], got["dL_dsh"][:, 0], rtol=1e-3, atol=1e-3 * np.abs(got["dL_dsh"]).max())
+    if M > 1:
+        np.testing.assert_allclose(fused["d_features_rest"], got["dL_dsh"][:, 1:], rtol=1e-3, atol=1e-3 * np.abs(got["dL_dsh"]).max())
