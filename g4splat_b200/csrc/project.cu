@@ -25,46 +25,86 @@ __device__ const float SH_C3[] = {-0.5900435899266435f, 2.890611442640554f, -0.4
                                   -0.5900435899266435f};
 
 // Degree-D real SH -> RGB for one Gaussian, + 0.5, clamp at 0 (CR/forward.cu:20-71).  Rounding pinned
-// to the reference's SASS: every term is accumulated with one fma(coef, sh, r); the coefficients are
-// rounded products, with xx*3 - yy, zz*4 - xx, 2zz - 3xx - 3yy and xx - 3yy fused as fma(.., +-3|4, ..).
+// to the reference's SASS: every term is accumulated with one fma(coef, sh, r) in ascending coefficient
+// order; the coefficients are rounded products, with xx*3 - yy, zz*4 - xx, 2zz - 3xx - 3yy and xx - 3yy fused
+// as fma(.., +-3|4, ..).  sh_basis() produces the 15 coefficients kf[1..15] (kf[0] is SH_C0 itself).
+__device__ __forceinline__ void sh_basis(int deg, f3 dir, float (&kf)[16]) {
+    if (deg > 0) {
+        const float x = dir.x, y = dir.y, z = dir.z;
+        kf[1] = -__fmul_rn(SH_C1, y);
+        kf[2] = __fmul_rn(SH_C1, z);
+        kf[3] = -__fmul_rn(SH_C1, x);
+        if (deg > 1) {
+            const float xx = __fmul_rn(x, x), yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+            const float xy = __fmul_rn(x, y), yz = __fmul_rn(y, z), xz = __fmul_rn(x, z);
+            const float zz2 = __fadd_rn(zz, zz), xx_yy = __fsub_rn(xx, yy);
+            kf[4] = __fmul_rn(SH_C2[0], xy);
+            kf[5] = __fmul_rn(SH_C2[1], yz);
+            kf[6] = __fmul_rn(SH_C2[2], __fsub_rn(__fsub_rn(zz2, xx), yy));
+            kf[7] = __fmul_rn(SH_C2[3], xz);
+            kf[8] = __fmul_rn(SH_C2[4], xx_yy);
+            if (deg > 2) {
+                const float zz4_xx_yy = __fsub_rn(__fmaf_rn(zz, 4.0f, -xx), yy);
+                kf[9] = __fmul_rn(__fmul_rn(SH_C3[0], y), __fmaf_rn(xx, 3.0f, -yy));
+                kf[10] = __fmul_rn(__fmul_rn(SH_C3[1], xy), z);
+                kf[11] = __fmul_rn(__fmul_rn(SH_C3[2], y), zz4_xx_yy);
+                kf[12] = __fmul_rn(__fmul_rn(SH_C3[3], z), __fmaf_rn(yy, -3.0f, __fmaf_rn(xx, -3.0f, zz2)));
+                kf[13] = __fmul_rn(__fmul_rn(SH_C3[4], x), zz4_xx_yy);
+                kf[14] = __fmul_rn(__fmul_rn(SH_C3[5], z), xx_yy);
+                kf[15] = __fmul_rn(__fmul_rn(SH_C3[6], x), __fmaf_rn(yy, -3.0f, xx));
+            }
+        }
+    }
+}
+__device__ __forceinline__ f3 sh_finish(f3 r, uint8_t& clamp_mask) {
+    r = mk3(__fadd_rn(r.x, 0.5f), __fadd_rn(r.y, 0.5f), __fadd_rn(r.z, 0.5f));
+    clamp_mask = (uint8_t)((r.x < 0 ? 1 : 0) | (r.y < 0 ? 2 : 0) | (r.z < 0 ? 4 : 0));
+    return mk3(fmaxf(r.x, 0.0f), fmaxf(r.y, 0.0f), fmaxf(r.z, 0.0f));
+}
 // Coefficient 0 is read from `sh0`, coefficients i >= 1 from `shr[3 (i - 1) ..]`: one [M][3] array
 // (shr = sh0 + 3) for the operator API, the trainer's separate _features_dc / _features_rest tensors
 // for the raw-parameter entry points.
 __device__ __forceinline__ f3 sh_to_rgb(int deg, const float* __restrict__ sh0, const float* __restrict__ shr, f3 dir,
                                         uint8_t& clamp_mask) {
+    float kf[16];
+    sh_basis(deg, dir, kf);
     f3 r = mk3(__fmul_rn(SH_C0, sh0[0]), __fmul_rn(SH_C0, sh0[1]), __fmul_rn(SH_C0, sh0[2]));
-    auto acc = [&](float k, int i) {
-        r.x = __fmaf_rn(k, shr[3 * i - 3], r.x); r.y = __fmaf_rn(k, shr[3 * i - 2], r.y); r.z = __fmaf_rn(k, shr[3 * i - 1], r.z);
+    const int n = (deg + 1) * (deg + 1);
+#pragma unroll
+    for (int i = 1; i < 16; i++) {
+        if (i < n) {
+            r.x = __fmaf_rn(kf[i], shr[3 * i - 3], r.x); r.y = __fmaf_rn(kf[i], shr[3 * i - 2], r.y); r.z = __fmaf_rn(kf[i], shr[3 * i - 1], r.z);
+        }
+    }
+    return sh_finish(r, clamp_mask);
+}
+// The same evaluation for a 16-byte aligned [16][3] row (the usual case: 192-byte rows of a torch tensor):
+// twelve 128-bit loads instead of 48 scalar ones, four coefficients per three loads, same order.
+__device__ __forceinline__ f3 sh_to_rgb_row16(int deg, const float4* __restrict__ s4, f3 dir, uint8_t& clamp_mask) {
+    float kf[16];
+    sh_basis(deg, dir, kf);
+    auto acc = [](f3& r, float k, float s0, float s1, float s2) {
+        r.x = __fmaf_rn(k, s0, r.x); r.y = __fmaf_rn(k, s1, r.y); r.z = __fmaf_rn(k, s2, r.z);
     };
+    float4 a = s4[0];
+    f3 r = mk3(__fmul_rn(SH_C0, a.x), __fmul_rn(SH_C0, a.y), __fmul_rn(SH_C0, a.z));
     if (deg > 0) {
-        const float x = dir.x, y = dir.y, z = dir.z;
-        acc(-__fmul_rn(SH_C1, y), 1);
-        acc(__fmul_rn(SH_C1, z), 2);
-        acc(-__fmul_rn(SH_C1, x), 3);
+        float4 b = s4[1], c = s4[2];
+        acc(r, kf[1], a.w, b.x, b.y); acc(r, kf[2], b.z, b.w, c.x); acc(r, kf[3], c.y, c.z, c.w);
         if (deg > 1) {
-            const float xx = __fmul_rn(x, x), yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
-            const float xy = __fmul_rn(x, y), yz = __fmul_rn(y, z), xz = __fmul_rn(x, z);
-            const float zz2 = __fadd_rn(zz, zz), xx_yy = __fsub_rn(xx, yy);
-            acc(__fmul_rn(SH_C2[0], xy), 4);
-            acc(__fmul_rn(SH_C2[1], yz), 5);
-            acc(__fmul_rn(SH_C2[2], __fsub_rn(__fsub_rn(zz2, xx), yy)), 6);
-            acc(__fmul_rn(SH_C2[3], xz), 7);
-            acc(__fmul_rn(SH_C2[4], xx_yy), 8);
+            a = s4[3]; b = s4[4]; c = s4[5];
+            acc(r, kf[4], a.x, a.y, a.z); acc(r, kf[5], a.w, b.x, b.y); acc(r, kf[6], b.z, b.w, c.x); acc(r, kf[7], c.y, c.z, c.w);
+            a = s4[6];
+            acc(r, kf[8], a.x, a.y, a.z);
             if (deg > 2) {
-                const float zz4_xx_yy = __fsub_rn(__fmaf_rn(zz, 4.0f, -xx), yy);
-                acc(__fmul_rn(__fmul_rn(SH_C3[0], y), __fmaf_rn(xx, 3.0f, -yy)), 9);
-                acc(__fmul_rn(__fmul_rn(SH_C3[1], xy), z), 10);
-                acc(__fmul_rn(__fmul_rn(SH_C3[2], y), zz4_xx_yy), 11);
-                acc(__fmul_rn(__fmul_rn(SH_C3[3], z), __fmaf_rn(yy, -3.0f, __fmaf_rn(xx, -3.0f, zz2))), 12);
-                acc(__fmul_rn(__fmul_rn(SH_C3[4], x), zz4_xx_yy), 13);
-                acc(__fmul_rn(__fmul_rn(SH_C3[5], z), xx_yy), 14);
-                acc(__fmul_rn(__fmul_rn(SH_C3[6], x), __fmaf_rn(yy, -3.0f, xx)), 15);
+                b = s4[7]; c = s4[8];
+                acc(r, kf[9], a.w, b.x, b.y); acc(r, kf[10], b.z, b.w, c.x); acc(r, kf[11], c.y, c.z, c.w);
+                a = s4[9]; b = s4[10]; c = s4[11];
+                acc(r, kf[12], a.x, a.y, a.z); acc(r, kf[13], a.w, b.x, b.y); acc(r, kf[14], b.z, b.w, c.x); acc(r, kf[15], c.y, c.z, c.w);
             }
         }
     }
-    r = mk3(__fadd_rn(r.x, 0.5f), __fadd_rn(r.y, 0.5f), __fadd_rn(r.z, 0.5f));
-    clamp_mask = (uint8_t)((r.x < 0 ? 1 : 0) | (r.y < 0 ? 2 : 0) | (r.z < 0 ? 4 : 0));
-    return mk3(fmaxf(r.x, 0.0f), fmaxf(r.y, 0.0f), fmaxf(r.z, 0.0f));
+    return sh_finish(r, clamp_mask);
 }
 
 // Bounding box (in pixels, inclusive, already padded) of every pixel for which this Gaussian can
@@ -171,30 +211,50 @@ __device__ __forceinline__ Activated activate(float2 s_raw, float4 r_raw, float 
 }
 
 // Per-thread part of the forward projection.  Returns false when the Gaussian is culled (radii 0).
+// ---- forward projection in two phases ---------------------------------------------------------------
+// Phase 1 (every Gaussian): view transform, frustum cull, T matrix, normal flip, 3-sigma radius, reference
+// tile rectangle.  Phase 2 (survivors only, ~1 in 4 at c2): colour from SH, contribution bounding box and
+// ellipse, culled tile rectangle, record.  Between the two the survivors of the CTA are compacted through
+// shared memory, so phase 2 -- two thirds of the instructions and all of the SH traffic -- runs on dense
+// warps instead of on 8 warps with 7 of 32 lanes alive.
+struct ProjGeo {                     // what phase 1 hands to phase 2 (PG_WORDS 32-bit words)
+    f3 Tu, Tv, Tw, normal;
+    float cx, cy, depth, opacity;    // opacity: activated opacity in raw mode, unused otherwise
+    int radius, rx0, ry0, rx1, ry1;  // reference tile rectangle (non-empty)
+};
+constexpr int PG_WORDS = 20;
+
 struct ProjOut {
-    f3 Tu, Tv, Tw, normal, rgb;
-    float cx, cy, opacity, depth;
+    f3 rgb;
+    float opacity;
     float4 bb, conic;
     float conic_By, rr2;
-    int radius, rx0, ry0, rx1, ry1;   // candidate tile rectangle: reference rect x contribution bbox (may be empty)
+    int rx0, ry0, rx1, ry1;          // culled tile rectangle: reference rect x contribution bbox (may be empty)
     uint8_t clamp_mask;
 };
+
 template <bool RAW>
-__device__ __forceinline__ bool project_one(const ProjectArgs& a, int idx, ProjOut& o) {
+__device__ __forceinline__ bool project_geometry(const ProjectArgs& a, int idx, ProjGeo& o) {
     const f3 p = mk3(a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]);
+    // scale and rotation are fetched together with the mean, before the frustum test decides whether they
+    // are needed: one memory round trip per Gaussian instead of two (24 wasted bytes for a culled one)
+    float2 sc = make_float2(0.f, 0.f);
+    float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
+    if (a.transMat_precomp == nullptr) {
+        sc = ((const float2*)a.scales)[idx];
+        q = ((const float4*)a.rotations)[idx];
+    }
     const f3 pv = xform_point_4x3(p, a.view);
     if (pv.z <= 0.2f) {  // in_frustum (CR/auxiliary.h:199)
         if (a.prefiltered) atomicAdd(&a.counters[CNT_PREFILTER_VIOLATION], 1);
         return false;
     }
     f3 Tu, Tv, Tw, normal;
-    float opacity_act = 0.0f;
+    o.opacity = 0.0f;
     if (a.transMat_precomp == nullptr) {
-        float2 sc = ((const float2*)a.scales)[idx];
-        float4 q = ((const float4*)a.rotations)[idx];
         if (RAW) {
             const Activated act = activate(sc, q, a.opacities[idx], a.mip_filter, idx);
-            sc = act.scale; q = act.rot; opacity_act = act.opacity;
+            sc = act.scale; q = act.rot; o.opacity = act.opacity;
         }
         f3 R[3];
         quat_to_R(q, R);
@@ -232,15 +292,23 @@ __device__ __forceinline__ bool project_one(const ProjectArgs& a, int idx, ProjO
     // getRect (CR/auxiliary.h:66-76)
     const int max_radius = (int)radius;
     const int gx = a.grid_x, gy = a.grid_y;
-    int rx0 = min(gx, max(0, (int)((cx - max_radius) / TILE)));
-    int ry0 = min(gy, max(0, (int)((cy - max_radius) / TILE)));
-    int rx1 = min(gx, max(0, (int)((cx + max_radius + TILE - 1) / TILE)));
-    int ry1 = min(gy, max(0, (int)((cy + max_radius + TILE - 1) / TILE)));
+    const int rx0 = min(gx, max(0, (int)((cx - max_radius) / TILE)));
+    const int ry0 = min(gy, max(0, (int)((cy - max_radius) / TILE)));
+    const int rx1 = min(gx, max(0, (int)((cx + max_radius + TILE - 1) / TILE)));
+    const int ry1 = min(gy, max(0, (int)((cy + max_radius + TILE - 1) / TILE)));
     if ((rx1 - rx0) * (ry1 - ry0) == 0) return false;
+    o.Tu = Tu; o.Tv = Tv; o.Tw = Tw; o.normal = normal;
+    o.cx = cx; o.cy = cy; o.depth = pv.z; o.radius = max_radius;
+    o.rx0 = rx0; o.ry0 = ry0; o.rx1 = rx1; o.ry1 = ry1;
+    return true;
+}
 
+template <bool RAW>
+__device__ __forceinline__ void project_appearance(const ProjectArgs& a, int idx, const ProjGeo& g, ProjOut& o) {
     // colour
     o.clamp_mask = 0;
     if (a.colors_precomp == nullptr) {
+        const f3 p = mk3(a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]);
         f3 dir = sub3(p, mk3(a.campos[0], a.campos[1], a.campos[2]));
         const float len = __fsqrt_rn(dot3_rn(dir.x, dir.x, dir.y, dir.y, dir.z, dir.z));
         dir = mk3(__fdiv_rn(dir.x, len), __fdiv_rn(dir.y, len), __fdiv_rn(dir.z, len));
@@ -248,15 +316,19 @@ __device__ __forceinline__ bool project_one(const ProjectArgs& a, int idx, ProjO
             o.rgb = sh_to_rgb(a.D, a.shs + (size_t)idx * 3, a.sh_rest + (size_t)idx * (a.M - 1) * 3, dir, o.clamp_mask);
         } else {
             const float* sh = a.shs + (size_t)idx * a.M * 3;
-            o.rgb = sh_to_rgb(a.D, sh, sh + 3, dir, o.clamp_mask);
+            if (a.M == 16 && (reinterpret_cast<uintptr_t>(a.shs) & 15) == 0)
+                o.rgb = sh_to_rgb_row16(a.D, reinterpret_cast<const float4*>(sh), dir, o.clamp_mask);
+            else
+                o.rgb = sh_to_rgb(a.D, sh, sh + 3, dir, o.clamp_mask);
         }
     } else {
         o.rgb = mk3(a.colors_precomp[3 * idx], a.colors_precomp[3 * idx + 1], a.colors_precomp[3 * idx + 2]);
     }
-    o.opacity = RAW ? opacity_act : a.opacities[idx];
+    o.opacity = RAW ? g.opacity : a.opacities[idx];
 
     // exact culling, step 1: tiles of the reference rectangle that hold a pixel of the contribution bbox
-    const bool can_contribute = contribution_bbox(Tu, Tv, Tw, cx, cy, o.opacity, o.bb, o.conic, o.conic_By, o.rr2);
+    int rx0 = g.rx0, ry0 = g.ry0, rx1 = g.rx1, ry1 = g.ry1;
+    const bool can_contribute = contribution_bbox(g.Tu, g.Tv, g.Tw, g.cx, g.cy, o.opacity, o.bb, o.conic, o.conic_By, o.rr2);
     if (can_contribute) {
         // tile t covers pixels [16 t, 16 t + 15]
         const float fx0 = fmaxf(ceilf((o.bb.x - (TILE - 1)) / TILE), (float)rx0);
@@ -266,33 +338,80 @@ __device__ __forceinline__ bool project_one(const ProjectArgs& a, int idx, ProjO
         rx0 = (int)fx0; ry0 = (int)fy0; rx1 = (int)fx1; ry1 = (int)fy1;
     }
     if (!can_contribute || rx1 <= rx0 || ry1 <= ry0) { rx0 = ry0 = rx1 = ry1 = 0; }
-    o.Tu = Tu; o.Tv = Tv; o.Tw = Tw; o.normal = normal;
-    o.cx = cx; o.cy = cy; o.depth = pv.z; o.radius = max_radius;
     o.rx0 = rx0; o.ry0 = ry0; o.rx1 = rx1; o.ry1 = ry1;
-    return true;
 }
 
-// Forward projection.  One thread per Gaussian for the arithmetic; the per-tile work (exact
-// ellipse-vs-tile test, per-tile counters) is then done warp-cooperatively: for each visible
-// Gaussian of the warp in turn, the 32 lanes take 32 tiles of its rectangle, so long rectangles
-// (close-up splats cover thousands of tiles) do not serialise on one thread, and the surviving-
-// tile mask of small rectangles is simply the ballot.
+// One thread per Gaussian for the arithmetic; the per-tile counting of phase 2 is warp-cooperative: for
+// each Gaussian of the warp with a long rectangle in turn, the 32 lanes take 32 tiles of it, so close-up
+// splats that cover thousands of tiles do not serialise on one thread.
+constexpr int PF_THREADS = 256;
 template <bool RAW>
-__global__ void __launch_bounds__(256) project_fwd_kernel(ProjectArgs a) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(PF_THREADS, 4) project_fwd_kernel(ProjectArgs a) {
+    __shared__ uint32_t s_geo[PG_WORDS][PF_THREADS];   // SoA: slot-major reads and writes are conflict-free
+    __shared__ int s_wcount[PF_THREADS / 32];
+    const int idx = blockIdx.x * PF_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // ---- phase 1 ------------------------------------------------------------------------------
+    ProjGeo g;
+    const bool visible = idx < a.P && project_geometry<RAW>(a, idx, g);
+    if (idx < a.P) {
+        a.radii[idx] = visible ? g.radius : 0;
+        if (!visible) a.geom.ntiles[idx] = 0u;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, visible);
+    if (lane == 0) s_wcount[warp] = __popc(bal);
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < PF_THREADS / 32; w++) {
+        const int c = s_wcount[w];
+        if (w < warp) base += c;
+        total += c;
+    }
+    if (visible) {
+        const int slot = base + __popc(bal & ((1u << lane) - 1u));
+        const float f[15] = {g.Tu.x, g.Tu.y, g.Tu.z, g.Tv.x, g.Tv.y, g.Tv.z, g.Tw.x, g.Tw.y, g.Tw.z,
+                             g.normal.x, g.normal.y, g.normal.z, g.cx, g.cy, g.depth};
+#pragma unroll
+        for (int k = 0; k < 15; k++) s_geo[k][slot] = __float_as_uint(f[k]);
+        s_geo[15][slot] = __float_as_uint(g.opacity);
+        s_geo[16][slot] = (uint32_t)g.radius;
+        s_geo[17][slot] = (uint32_t)g.rx0 | ((uint32_t)g.ry0 << 16);
+        s_geo[18][slot] = (uint32_t)g.rx1 | ((uint32_t)g.ry1 << 16);
+        s_geo[19][slot] = (uint32_t)idx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && total > 0) atomicAdd(&a.counters[CNT_VISIBLE], total);
+
+    // ---- phase 2: thread t takes the t-th survivor of the CTA ---------------------------------------
+    const int t = threadIdx.x;
+    const bool active = t < total;
+    if (__ballot_sync(0xffffffffu, active) == 0u) return;   // whole warp idle
     ProjOut o;
     o.rx0 = o.ry0 = o.rx1 = o.ry1 = 0;
-    const bool visible = idx < a.P && project_one<RAW>(a, idx, o);
+    int id2 = 0;
+    if (active) {
+        float f[15];
+#pragma unroll
+        for (int k = 0; k < 15; k++) f[k] = __uint_as_float(s_geo[k][t]);
+        g.Tu = mk3(f[0], f[1], f[2]); g.Tv = mk3(f[3], f[4], f[5]); g.Tw = mk3(f[6], f[7], f[8]);
+        g.normal = mk3(f[9], f[10], f[11]); g.cx = f[12]; g.cy = f[13]; g.depth = f[14];
+        g.opacity = __uint_as_float(s_geo[15][t]);
+        g.radius = (int)s_geo[16][t];
+        const uint32_t r0 = s_geo[17][t], r1 = s_geo[18][t];
+        g.rx0 = (int)(r0 & 0xffffu); g.ry0 = (int)(r0 >> 16); g.rx1 = (int)(r1 & 0xffffu); g.ry1 = (int)(r1 >> 16);
+        id2 = (int)s_geo[19][t];
+        project_appearance<RAW>(a, id2, g, o);
+    }
     const int gx = a.grid_x;
-    const int my_w = o.rx1 - o.rx0, my_total = visible ? my_w * (o.ry1 - o.ry0) : 0;
+    const int my_w = o.rx1 - o.rx0, my_total = active ? my_w * (o.ry1 - o.ry0) : 0;
     // per-tile counters.  Rectangles of up to 32 tiles are counted by their own lane (fire-and-forget
     // reductions); longer ones (close-up splats cover thousands of tiles) by the whole warp.
     // (An exact ellipse-vs-tile test here was measured: it removes ~12 % of the instances of this
     // workload but costs more in this kernel than it saves downstream; the blend kernel applies the
     // same test per 8x4 region, where it is nearly free.)
     constexpr int SERIAL_TILES = 32;
-    const int my_nt = my_total;
     if (my_total > 0 && my_total <= SERIAL_TILES) {
         for (int y = o.ry0; y < o.ry1; y++)
             for (int x = o.rx0; x < o.rx1; x++) atomicAdd(&a.tile_count[y * gx + x], 1u);
@@ -302,29 +421,26 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(ProjectArgs a) {
         const int src = __ffs(pending) - 1;
         pending &= pending - 1;
         const int rx0 = __shfl_sync(0xffffffffu, o.rx0, src), ry0 = __shfl_sync(0xffffffffu, o.ry0, src);
-        const int w = __shfl_sync(0xffffffffu, my_w, src), total = __shfl_sync(0xffffffffu, my_total, src);
-        for (int i = lane; i < total; i += 32) {
+        const int w = __shfl_sync(0xffffffffu, my_w, src), tot = __shfl_sync(0xffffffffu, my_total, src);
+        for (int i = lane; i < tot; i += 32) {
             const int iy = i / w, ix = i - iy * w;
             atomicAdd(&a.tile_count[(ry0 + iy) * gx + rx0 + ix], 1u);
         }
     }
-    if (idx >= a.P) return;
-    a.radii[idx] = visible ? o.radius : 0;
-    a.geom.ntiles[idx] = (uint32_t)my_nt;
-    if (!visible) return;
-    if (my_nt == 0) { o.rx0 = o.ry0 = o.rx1 = o.ry1 = 0; o.bb = make_float4(1e30f, 1e30f, -1e30f, -1e30f); }
-    float4* rec = a.geom.rec + (size_t)idx * REC_F4;
+    if (!active) return;
+    a.geom.ntiles[id2] = (uint32_t)my_total;
+    if (my_total == 0) { o.rx0 = o.ry0 = o.rx1 = o.ry1 = 0; o.bb = make_float4(1e30f, 1e30f, -1e30f, -1e30f); }
+    float4* rec = a.geom.rec + (size_t)id2 * REC_F4;
     rec[0] = o.bb;
-    rec[1] = make_float4(o.Tu.x, o.Tu.y, o.Tu.z, o.Tv.x);
-    rec[2] = make_float4(o.Tv.y, o.Tv.z, o.Tw.x, o.Tw.y);
-    rec[3] = make_float4(o.Tw.z, o.cx, o.cy, o.opacity);
-    rec[4] = make_float4(o.normal.x, o.normal.y, o.normal.z, o.rgb.x);
+    rec[1] = make_float4(g.Tu.x, g.Tu.y, g.Tu.z, g.Tv.x);
+    rec[2] = make_float4(g.Tv.y, g.Tv.z, g.Tw.x, g.Tw.y);
+    rec[3] = make_float4(g.Tw.z, g.cx, g.cy, o.opacity);
+    rec[4] = make_float4(g.normal.x, g.normal.y, g.normal.z, o.rgb.x);
     rec[5] = make_float4(o.rgb.y, o.rgb.z, o.conic_By, o.rr2);
     rec[6] = o.conic;
-    a.geom.depth[idx] = o.depth;
-    a.geom.clamped[idx] = o.clamp_mask;
-    a.geom.rect[idx] = make_ushort4((unsigned short)o.rx0, (unsigned short)o.ry0, (unsigned short)o.rx1, (unsigned short)o.ry1);
-    atomicAdd(&a.counters[CNT_VISIBLE], 1);
+    a.geom.depth[id2] = g.depth;
+    a.geom.clamped[id2] = o.clamp_mask;
+    a.geom.rect[id2] = make_ushort4((unsigned short)o.rx0, (unsigned short)o.ry0, (unsigned short)o.rx1, (unsigned short)o.ry1);
 }
 
 // One (Gaussian, tile) instance per surviving tile: key = depth bits << 32 | Gaussian id, written
@@ -700,8 +816,9 @@ void launch_densify_stats(int P, const float* dL_dmeans2D, const int* radii, flo
 }
 void launch_project_fwd(const ProjectArgs& a, cudaStream_t s) {
     if (a.P <= 0) return;
-    if (a.raw) project_fwd_kernel<true><<<(a.P + 255) / 256, 256, 0, s>>>(a);
-    else project_fwd_kernel<false><<<(a.P + 255) / 256, 256, 0, s>>>(a);
+    const int blocks = (a.P + PF_THREADS - 1) / PF_THREADS;
+    if (a.raw) project_fwd_kernel<true><<<blocks, PF_THREADS, 0, s>>>(a);
+    else project_fwd_kernel<false><<<blocks, PF_THREADS, 0, s>>>(a);
     count_launch();
 }
 void launch_scatter(const ScatterArgs& a, cudaStream_t s) {
