@@ -445,8 +445,10 @@ __global__ void __launch_bounds__(PF_THREADS, 4) project_fwd_kernel(ProjectArgs 
 
 // One (Gaussian, tile) instance per surviving tile: key = depth bits << 32 | Gaussian id, written
 // to an arbitrary free slot of the tile's bucket; the per-tile sort orders the bucket afterwards.
-// Warp-cooperative like the counting above: the lanes take the tiles of one Gaussian at a time,
-// so 32 cursor atomics (which return a value) are in flight instead of one.
+// The instances of a warp's 32 Gaussians are spread evenly over its lanes: an exclusive scan of the tile
+// counts numbers them, lane l takes instances l, l + 32, ... and finds the owning Gaussian by searching
+// the scan, so all cursor atomics of the warp (they return a value: ~1 us each) are in flight together
+// instead of one Gaussian after the other.
 __global__ void __launch_bounds__(256) scatter_kernel(ScatterArgs a) {
     if ((int64_t)a.counters[CNT_RENDERED] > a.capacity) return;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -458,17 +460,36 @@ __global__ void __launch_bounds__(256) scatter_kernel(ScatterArgs a) {
         r = a.geom.rect[idx];
         key = (((unsigned long long)__float_as_uint(a.geom.depth[idx])) << 32) | (unsigned long long)(uint32_t)idx;
     }
+    if (__ballot_sync(0xffffffffu, live) == 0u) return;
     const int my_w = r.z - r.x, my_total = my_w * (r.w - r.y);
-    unsigned pending = __ballot_sync(0xffffffffu, live);
-    while (pending) {
-        const int src = __ffs(pending) - 1;
-        pending &= pending - 1;
-        const int rx0 = __shfl_sync(0xffffffffu, (int)r.x, src), ry0 = __shfl_sync(0xffffffffu, (int)r.y, src);
-        const int w = __shfl_sync(0xffffffffu, my_w, src), total = __shfl_sync(0xffffffffu, my_total, src);
-        const unsigned long long k = __shfl_sync(0xffffffffu, key, src);
-        for (int i = lane; i < total; i += 32) {
-            const int iy = i / w, ix = i - iy * w;
-            const int t = (ry0 + iy) * a.grid_x + rx0 + ix;
+    // inclusive scan of the instance counts over the warp
+    int incl = my_total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+    const int excl = incl - my_total;
+    for (int i = lane; i - lane < warp_total; i += 32) {   // uniform trip count: the shuffles below need every lane
+        // owner = the last lane whose exclusive offset is <= i (binary search over the scan by shuffles)
+        int lo = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const int probe = lo + step;
+            const int e = __shfl_sync(0xffffffffu, excl, probe & 31);
+            if (probe < 32 && e <= i) lo = probe;
+        }
+        // (lanes with my_total == 0 share their offset with the next live lane: the search lands on the
+        //  last of them, i.e. on the live one, because it takes the LAST lane with excl <= i)
+        const int o_excl = __shfl_sync(0xffffffffu, excl, lo);
+        const int o_w = __shfl_sync(0xffffffffu, my_w, lo);
+        const int o_x0 = __shfl_sync(0xffffffffu, (int)r.x, lo), o_y0 = __shfl_sync(0xffffffffu, (int)r.y, lo);
+        const unsigned long long k = __shfl_sync(0xffffffffu, key, lo);
+        if (i < warp_total) {
+            const int j = i - o_excl;
+            const int iy = j / o_w, ix = j - iy * o_w;
+            const int t = (o_y0 + iy) * a.grid_x + o_x0 + ix;
             const uint32_t slot = a.tile_offset[t] + atomicAdd(&a.tile_cursor[t], 1u);
             a.keys[slot] = k;
         }
