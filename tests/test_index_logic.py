@@ -1,0 +1,68 @@
+"""Index logic of two kernels restated in Python and checked exhaustively / on random inputs (no GPU):
+the register bitonic network of `tile_sort_warp_kernel` and the owner search of `scatter_kernel`
+(g4splat_b200/csrc/binning.cu, project.cu).  The GPU parity tests check the kernels themselves; these keep
+the reasoning behind their index arithmetic executable."""
+import random
+
+
+def warp_bitonic(keys, nreg):
+    """binning.cu: warp_bitonic_sort<NREG> -- element e = r * 32 + lane lives in register r of its lane."""
+    n_total = nreg * 32
+    pad = (1 << 64) - 1
+    key = [[keys[r * 32 + l] if r * 32 + l < len(keys) else pad for l in range(32)] for r in range(nreg)]
+    k = 2
+    while k <= n_total:
+        j = k >> 1
+        while j > 0:
+            if j >= 32:                                   # partner = another register of the same lane
+                jr = j >> 5
+                for r in range(nreg):
+                    if (r & jr) == 0:
+                        asc = ((r * 32) & k) == 0
+                        for lane in range(32):
+                            x, y = key[r][lane], key[r | jr][lane]
+                            if (x > y) if asc else (x < y):
+                                key[r][lane], key[r | jr][lane] = y, x
+            else:                                         # partner = lane ^ j, reached with a shuffle
+                for r in range(nreg):
+                    new = [None] * 32
+                    for lane in range(32):
+                        lower = (lane & j) == 0
+                        asc = (((r * 32) & k) == 0) if k >= 32 else ((lane & k) == 0)
+                        x, y = key[r][lane], key[r][lane ^ j]
+                        new[lane] = min(x, y) if lower == asc else max(x, y)
+                    key[r] = new
+            j >>= 1
+        k <<= 1
+    return [key[e // 32][e % 32] for e in range(len(keys))]
+
+
+def test_warp_bitonic_network_sorts_every_length():
+    rng = random.Random(1)
+    for nreg in (1, 2, 4, 8):
+        for n in sorted({1, 2, 31, 32, 33, 63, 64, 65, 100, 127, 128, 129, 200, 255, 256} & set(range(1, nreg * 32 + 1))):
+            keys = [rng.getrandbits(60) for _ in range(n)]
+            assert warp_bitonic(keys, nreg) == sorted(keys), (nreg, n)
+    # equal depths: (depth << 32 | index) keys are distinct, ties in depth resolve by index
+    keys = [(7 << 32) | i for i in rng.sample(range(1000), 200)]
+    assert warp_bitonic(keys, 8) == sorted(keys)
+
+
+def scatter_owner(excl, i):
+    """project.cu: scatter_kernel -- the last lane whose exclusive offset is <= i, by binary search."""
+    lo = 0
+    for step in (16, 8, 4, 2, 1):
+        probe = lo + step
+        if probe < 32 and excl[probe & 31] <= i:
+            lo = probe
+    return lo
+
+
+def test_scatter_owner_search_lands_on_the_live_lane():
+    rng = random.Random(3)
+    for _ in range(500):
+        counts = [rng.choice([0, 0, 0, 1, 2, 5, 9, 40, 700]) for _ in range(32)]
+        excl = [sum(counts[:l]) for l in range(32)]
+        for i in range(sum(counts)):
+            lane = scatter_owner(excl, i)
+            assert counts[lane] > 0 and excl[lane] <= i < excl[lane] + counts[lane]
