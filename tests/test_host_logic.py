@@ -188,3 +188,31 @@ def test_loss_window_is_the_reference_gaussian():
     ref = ref / ref.sum()
     assert torch.equal(LU.gaussian(), ref) and len(LU._WINDOW_C) == 11
     assert all(float(LU._WINDOW_C[i]) == float(ref[i]) for i in range(11))
+
+
+def test_capacity_policy_buckets():
+    """Sticky, bucketed instance capacity (operator shim): a bucket holds the request, wastes < 25 % above
+    2^16, is monotone, and the policy only moves when the request outgrows it or shrinks four-fold."""
+    import g4splat_b200.diff_surfel_rasterization as op
+    bucket = op._CapacityPolicy.bucket
+    prev = 0
+    for n in list(range(1, 70000, 997)) + [2 ** k + d for k in range(16, 31) for d in (-1, 0, 1, 12345)]:
+        b = bucket(n)
+        assert b >= n and b >= 1 << 16
+        if n >= 1 << 16:
+            assert b < n * 1.25 + 1
+    for n in sorted(range(1 << 16, 1 << 22, 4093)):
+        assert bucket(n) >= prev
+        prev = bucket(n)
+    pol = op._CapacityPolicy()
+    assert pol.guess(0, 1_000_000) == bucket(6_000_000)        # first call: 6 instances per Gaussian
+    pol.observe(0, 1_300_000)
+    first = pol.guess(0, 1_000_000)
+    assert first >= 1_300_000 * 1.5
+    pol.observe(0, 1_250_000)                                    # smaller view: capacity stays (same allocator block)
+    assert pol.guess(0, 1_000_000) == first
+    pol.observe(0, 2_450_000)                                    # larger view: grows
+    assert pol.guess(0, 1_000_000) >= 2_450_000 * 1.5 > first
+    grown = pol.guess(0, 1_000_000)
+    pol.observe(0, 100_000)                                      # four-fold smaller: shrinks
+    assert pol.guess(0, 1_000_000) < grown
