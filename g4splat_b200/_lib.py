@@ -14,6 +14,8 @@ _vp, _i, _f, _i64, _sz, _d = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size
 SIGNATURES = {
     "g4s_version": (_i, []),
     "g4s_last_error": (C.c_char_p, []),
+    "g4s_set_fast_math": (_i, [_i]),
+    "g4s_get_fast_math": (_i, []),
     "g4s_launch_count": (_i64, []),
     "g4s_geom_bytes": (_sz, [_i]),
     "g4s_image_bytes": (_sz, [_i, _i]),

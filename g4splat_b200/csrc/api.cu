@@ -14,6 +14,9 @@ namespace g4s {
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 static thread_local std::string g_error;
+// 0: the forward decides and blends with IEEE division / expf (bit-identical to the reference);
+// 1: rcp.approx / ex2.approx in the forward blend (opt-in, g4s_set_fast_math)
+static std::atomic<int> g_fast_math{0};
 
 static int fail(int code, const std::string& msg) {
     g_error = msg;
@@ -101,6 +104,8 @@ int g4s_profile_read(float* mean_ms_out, int64_t* count_out, int n) {
 }
 
 int g4s_version(void) { return G4S_VERSION; }
+int g4s_set_fast_math(int on) { return g_fast_math.exchange(on != 0 ? 1 : 0); }
+int g4s_get_fast_math(void) { return g_fast_math.load(); }
 const char* g4s_last_error(void) { return g_error.c_str(); }
 int64_t g4s_launch_count(void) { return (int64_t)g_launches.load(); }
 
@@ -244,6 +249,7 @@ int g4s_forward_render(int P, int W, int H, const float* background, const void*
     ba.tile_offset = img.tile_offset; ba.tile_order = img.tile_order; ba.list = bin.list; ba.masks = bin.masks; ba.rec = geom.rec;
     ba.bg = background; ba.final_T = img.final_T; ba.n_contrib = img.n_contrib;
     ba.out_color = out_color; ba.out_others = out_others; ba.counters = img.counters;
+    ba.fast_math = g_fast_math.load(std::memory_order_relaxed);
     { StageTimer tm(ST_BLEND_FWD, s); launch_blend_fwd(ba, s); }
     return stage_check(debug, s, "blend_fwd");
 }
@@ -290,6 +296,7 @@ static int backward_impl(int P, int D, int M, int W, int H, const float* backgro
     bb.list = bin.list; bb.masks = bin.masks;
     bb.rec = geom.rec; bb.bg = background; bb.final_T = img.final_T; bb.n_contrib = img.n_contrib;
     bb.dL_dpix = dL_dout_color; bb.dL_dothers = dL_dout_others; bb.acc = acc;
+    bb.counters = img.counters; bb.capacity = capacity;
     { StageTimer tm(ST_BLEND_BWD, s); launch_blend_bwd(bb, s); }
     if ((rc = stage_check(debug, s, "blend_bwd"))) return rc;
 
@@ -360,13 +367,21 @@ int g4s_mark_visible(int P, const float* means3D, const float* viewmatrix, const
     return stage_check(false, (cudaStream_t)stream, "mark_visible");
 }
 
-int g4s_densify_stats(int P, const float* dL_dmeans2D, const int* radii, float* accum, float* denom,
-                      int* max_radii, void* stream) {
+static int densify_stats_impl(int P, const float* dL_dmeans2D, const int* radii, float* accum, float* denom,
+                              int* max_radii, int multimem, void* stream) {
     if (P < 0) return fail(G4S_EINVAL, "g4s_densify_stats: bad P");
     if (P == 0) return G4S_OK;
     if (!dL_dmeans2D || !radii || !accum || !denom || !max_radii) return fail(G4S_EINVAL, "g4s_densify_stats: null buffer");
-    launch_densify_stats(P, dL_dmeans2D, radii, accum, denom, max_radii, (cudaStream_t)stream);
+    launch_densify_stats(P, dL_dmeans2D, radii, accum, denom, max_radii, multimem, (cudaStream_t)stream);
     return stage_check(false, (cudaStream_t)stream, "densify_stats");
+}
+int g4s_densify_stats(int P, const float* dL_dmeans2D, const int* radii, float* accum, float* denom,
+                      int* max_radii, void* stream) {
+    return densify_stats_impl(P, dL_dmeans2D, radii, accum, denom, max_radii, 0, stream);
+}
+int g4s_densify_stats_multimem(int P, const float* dL_dmeans2D, const int* radii, float* accum_mc, float* denom_mc,
+                               int* max_radii_mc, void* stream) {
+    return densify_stats_impl(P, dL_dmeans2D, radii, accum_mc, denom_mc, max_radii_mc, 1, stream);
 }
 
 int g4s_photometric_forward(int W, int H, int C, const float* image, const float* gt, const float* window11,
@@ -480,7 +495,7 @@ __global__ void pair_stats_kernel(int W, int H, int grid_x, const uint32_t* tile
     for (int pos = lane; pos < min(n, warp_last); pos += 32) {
         const float4 bb = rec[(size_t)list[off + pos] * REC_F4];
         if (bb.x <= rx1 && bb.z >= rx0 && bb.y <= ry1 && bb.w >= ry0) {
-            const uint32_t m = masks[(size_t)(off + pos) * 8 + warp];
+            const uint32_t m = masks[(size_t)off * 8 + (size_t)warp * n + pos];
             blended += __popc(m);
             issued += m ? 32 : 0;
         }

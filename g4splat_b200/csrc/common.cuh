@@ -102,7 +102,7 @@ __host__ __device__ inline size_t image_layout(int W, int H, char* base, ImageVi
 // Binning buffer (per instance).
 struct BinView {
     uint32_t* list;            // [cap]     gaussian ids, per tile sorted by (depth, id)
-    uint32_t* masks;           // [cap][8]  per (instance, warp of the tile): lanes that blended it in the forward
+    uint32_t* masks;           // [cap * 8] per tile [8 regions][n entries]: lanes of the region that blended the entry (forward)
     unsigned long long* keys;  // [cap]     depth_bits << 32 | gaussian, bucketed by tile, unsorted
 };
 __host__ __device__ inline size_t bin_layout(int64_t cap, char* base, BinView* v) {

@@ -58,7 +58,8 @@ struct BlendFwdArgs {
     const uint32_t* tile_offset;
     const uint32_t* tile_order;
     const uint32_t* list;
-    uint32_t* masks;       // [cap][8] written: lanes of warp w that blended instance i
+    uint32_t* masks;       // [cap * 8] written, per tile [8 regions][n entries]: lanes of region w that blended entry j
+    int fast_math;         // 0: IEEE division / expf, bit-identical to the reference; 1: rcp.approx / ex2.approx
     const float4* rec;
     const float* bg;
     float* final_T;        // [3][N]
@@ -82,10 +83,13 @@ struct BlendBwdArgs {
     const float* dL_dpix;     // [3][N]
     const float* dL_dothers;  // [7][N]
     float4* acc;              // [P][5], zeroed by the caller
+    const int32_t* counters;
+    int64_t capacity;
 };
 void launch_blend_bwd(const BlendBwdArgs& a, cudaStream_t s);
 
-enum { ACC_MEANS3D = 1, ACC_SH = 2, ACC_OPACITY = 4, ACC_SCALES = 8, ACC_ROTATIONS = 16 };
+enum { ACC_MEANS3D = 1, ACC_SH = 2, ACC_OPACITY = 4, ACC_SCALES = 8, ACC_ROTATIONS = 16,
+       ACC_MULTIMEM = 32 /* the accumulated outputs are NVSwitch multicast addresses: multimem.red */ };
 struct ProjectBwdArgs {
     int P, D, M;
     int raw; const float* sh_rest; const float* opacities; const float* mip_filter; float* dL_dsh_rest;  // see ProjectArgs
@@ -103,7 +107,7 @@ void launch_project_bwd(const ProjectBwdArgs& a, cudaStream_t s);
 void launch_acc_clear(int P, const int* radii, float4* acc, cudaStream_t s);
 
 void launch_densify_stats(int P, const float* dL_dmeans2D, const int* radii, float* accum, float* denom,
-                          int* max_radii, cudaStream_t s);
+                          int* max_radii, int multimem, cudaStream_t s);
 void launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s);
 
 // ---- compute_mip_filter (gaussian_model.cu) ---------------------------------------------------

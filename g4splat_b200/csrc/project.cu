@@ -558,6 +558,24 @@ __device__ __forceinline__ f3 sh_backward(int deg, int M, const float* __restric
 // Gaussians, then the warp streams them out with fully coalesced stores (128-bit for the SH
 // block, which is 2/3 of the bytes): a thread-per-Gaussian store would scatter every 4-byte
 // word of a warp over 32 different cache lines.
+// Reductions into a running multi-view / multi-rank sum.  MC == false: the destination is ordinary device
+// memory (RED).  MC == true: the destination is an NVSwitch MULTICAST address that maps the same buffer of
+// every rank (view_parallel, transport "multimem"): one multimem.red adds the value into all replicas inside
+// the switch, so the per-step gradient all-reduce disappears into the kernel that produces the gradient.
+__device__ __forceinline__ void red_add(float* p, float v, bool mc) {
+    if (mc) asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+    else atomicAdd(p, v);   // result unused: fire-and-forget RED
+}
+__device__ __forceinline__ void red_add4(float* p, float4 v, bool mc) {
+    if (mc) asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                         ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    else atomicAdd(reinterpret_cast<float4*>(p), v);
+}
+__device__ __forceinline__ void red_max(int* p, int v, bool mc) {
+    if (mc) asm volatile("multimem.red.relaxed.sys.global.max.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    else atomicMax(p, v);
+}
+
 constexpr int PB_THREADS = 128;
 constexpr int PB_WARPS = PB_THREADS / 32;
 constexpr int PB_SMALL = 25;      // means3D 3, means2D 3, colors 3, opacity 1, scales 2, rots 4, transMat 9
@@ -729,13 +747,14 @@ __global__ void __launch_bounds__(PB_THREADS) project_bwd_kernel(ProjectBwdArgs 
     // buffer): rows of visible Gaussians are added to, rows of invisible ones are not touched at all.
     const int nvalid = min(32, a.P - warp_base);
     const unsigned vis_rows = __ballot_sync(0xffffffffu, visible);
+    const bool mc = (a.accumulate & ACC_MULTIMEM) != 0;
     auto stream_out = [&](float* dst, int width, int slot, bool accumulate) {
         float* g = dst + (size_t)warp_base * width;
         for (int e = lane; e < nvalid * width; e += 32) {
             const int row = e / width;
             const float v = s_small[warp][row * PB_SMALL + slot + (e - row * width)];
             if (!accumulate) g[e] = v;
-            else if ((vis_rows >> row) & 1u) atomicAdd(&g[e], v);  // result unused: fire-and-forget RED
+            else if ((vis_rows >> row) & 1u) red_add(&g[e], v, mc);
         }
     };
     stream_out(a.dL_dmeans3D, 3, 0, a.accumulate & ACC_MEANS3D);
@@ -758,7 +777,7 @@ __global__ void __launch_bounds__(PB_THREADS) project_bwd_kernel(ProjectBwdArgs 
                     c += 32;
                     while (c >= row) { c -= row; i++; }
                 }
-            } else if ((row & 3) == 0 && src_off == 0) {
+            } else if ((row & 3) == 0 && src_off == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
                 // running sum over views: only rows with a gradient are touched, 16 bytes per reduction
                 // (the row belongs to this warp alone; RED is used because it does not wait for the load)
                 const int quads = row >> 2;
@@ -767,11 +786,11 @@ __global__ void __launch_bounds__(PB_THREADS) project_bwd_kernel(ProjectBwdArgs 
                     const int k = f / quads, c4 = (f - k * quads) * 4;
                     const int r = __fns(sh_rows, 0, k + 1);   // k-th row with a gradient
                     const float* src = &s_sh[warp][r * PB_SH_STRIDE + c4];
-                    atomicAdd(reinterpret_cast<float4*>(g + (size_t)r * row + c4), make_float4(src[0], src[1], src[2], src[3]));
+                    red_add4(g + (size_t)r * row + c4, make_float4(src[0], src[1], src[2], src[3]), mc);
                 }
             } else {
                 for (int e = lane; e < total; e += 32) {
-                    if ((sh_rows >> i) & 1u) atomicAdd(&g[e], s_sh[warp][i * PB_SH_STRIDE + src_off + c]);
+                    if ((sh_rows >> i) & 1u) red_add(&g[e], s_sh[warp][i * PB_SH_STRIDE + src_off + c], mc);
                     c += 32;
                     while (c >= row) { c -= row; i++; }
                 }
@@ -798,17 +817,24 @@ __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* _
 // Densification bookkeeping the trainer runs after every backward (2DGS/scene/gaussian_model.py:
 // 649-651 add_densification_stats + train_with_refine_depth.py:583 max_radii2D), fused in one pass:
 //   visible = radii > 0;  accum += |dL_dmean2D.xy| on visible;  denom += visible;  max_radii = max(.)
+// multimem != 0: accum / denom / max_radii are multicast addresses (see red_add): every rank's replica is updated.
 __global__ void __launch_bounds__(256) densify_stats_kernel(int P, const float* __restrict__ dL_dmeans2D,
-                                                            const int* __restrict__ radii, float* __restrict__ accum,
-                                                            float* __restrict__ denom, int* __restrict__ max_radii) {
+                                                            const int* __restrict__ radii, float* accum,
+                                                            float* denom, int* max_radii, int multimem) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
     const int r = radii[idx];
     if (r > 0) {
         const float gx = dL_dmeans2D[3 * idx], gy = dL_dmeans2D[3 * idx + 1];
-        accum[idx] += sqrtf(gx * gx + gy * gy);
-        denom[idx] += 1.0f;
-        if (r > max_radii[idx]) max_radii[idx] = r;
+        if (multimem) {
+            red_add(&accum[idx], sqrtf(gx * gx + gy * gy), true);
+            red_add(&denom[idx], 1.0f, true);
+            red_max(&max_radii[idx], r, true);
+        } else {
+            accum[idx] += sqrtf(gx * gx + gy * gy);
+            denom[idx] += 1.0f;
+            if (r > max_radii[idx]) max_radii[idx] = r;
+        }
     }
 }
 
@@ -830,9 +856,9 @@ void launch_acc_clear(int P, const int* radii, float4* acc, cudaStream_t s) {
 
 // ---- launchers --------------------------------------------------------------------------------
 void launch_densify_stats(int P, const float* dL_dmeans2D, const int* radii, float* accum, float* denom,
-                          int* max_radii, cudaStream_t s) {
+                          int* max_radii, int multimem, cudaStream_t s) {
     if (P <= 0) return;
-    densify_stats_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, dL_dmeans2D, radii, accum, denom, max_radii);
+    densify_stats_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, dL_dmeans2D, radii, accum, denom, max_radii, multimem);
     count_launch();
 }
 void launch_project_fwd(const ProjectArgs& a, cudaStream_t s) {

@@ -58,6 +58,16 @@ enum {
 int g4s_version(void);
 const char* g4s_last_error(void);
 
+/* Arithmetic of the forward blend (process-wide; returns the previous setting).
+ *   0 (default)  IEEE division and expf in the reference's rounding sequence: colour, the seven allmap
+ *                channels and radii are bit-identical to the reference (CR/forward.cu:356-419).
+ *   1            rcp.approx / ex2.approx (2 ulp) for the ray-splat solve, the Gaussian weight and the NDC
+ *                depth: values within 1e-5; a pixel whose alpha, T < 1e-4 or T > 0.5 decision sits within an
+ *                ulp of its threshold may flip (north_star's 1e-4 parity with a counted flip budget,
+ *                tests/test_parity_gpu.py).  The backward is value-only and identical in both modes. */
+int g4s_set_fast_math(int on);
+int g4s_get_fast_math(void);
+
 /* ---- scratch sizes ------------------------------------------------------------------------- */
 /* per-Gaussian state (projected records, clamp masks, depths): reference GeometryState,
  * rasterizer_impl.cu:155-170 */
