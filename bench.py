@@ -43,8 +43,15 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "gaussians_per_s_fwd_bwd_1080p"
 UNIT = "Gaussians/s"
-CONFIG = "c2"
+CONFIG = "c2"           # default workload: the configuration BASELINE.json's metric is quoted on
 CAM_RING = 64
+# BASELINE.json configs 3-5: how a "step" is formed and how it scales with the rank count
+CONFIG_DOC = {
+    "c2": dict(name="c2: 1.0M surfels, SH degree 3, 1920x1080", scaling="weak", ring=64, step_views=None),
+    "c3": dict(name="c3: 2.5M surfels, SH degree 3, 1600x1200, 50 views per step sharded over the ranks",
+               scaling="strong", ring=50, step_views=50),
+    "c4": dict(name="c4: 5.0M surfels, SH degree 3, 1920x1080, 64 cameras", scaling="weak", ring=64, step_views=None),
+}
 
 
 # ------------------------------------------------------------------------------------------ util
@@ -156,19 +163,26 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
-def algorithmic_bytes(stage: str, P: int, V: int, R: int, N: int, T: int, K: int, M: int) -> float:
+def algorithmic_bytes(stage: str, P: int, V: int, R: int, N: int, T: int, K: int, M: int, sink: bool = True) -> float:
     """Compulsory bytes per launch of each stage (DESIGN.md 'Kernels'): every input read once,
-    every output written once, every (Gaussian, tile) instance written once and read once."""
+    every output written once, every (Gaussian, tile) instance written once and read once.
+    sink: project_bwd adds the rows of VISIBLE Gaussians into the multi-view sum (read-modify-write) and writes
+    no dense per-view gradient except dL_dmeans2D; otherwise it writes every row of every gradient tensor."""
     rec = 112 + 4 + 4 + 8 + 1                      # record + depth + ntiles + rect + clamp mask
+    g = 12 + 12 * M + 4 + 8 + 16                   # gradient row: means3D, SH, opacity, scales, rotations
+    if sink:
+        project_bwd = P * (4 + 12) + V * (80 + 48 + 40 + 12 * K + 2 * g)   # radii + dL_dmeans2D | acc, record, inputs, SH; RMW of the row
+    else:
+        project_bwd = P * (4 + 12 + g) + V * (80 + 48 + 40 + 12 * K)
     return {
         "project_fwd": P * (40 + 4) + V * (12 * K + rec) + R * 4,
         "tile_scan": T * 16,
         "scatter": V * 16 + R * (8 + 4),
         "tile_sort": R * (8 + 4) + T * 8,
-        "blend_fwd": R * (4 + 112 + 32) + N * 60 + T * 12,      # list + record gather + contribution masks
+        "blend_fwd": R * (4 + 32) + V * 112 + N * 60 + T * 12,   # list + masks written; each visible record once; images
         "acc_clear": P * 4 + V * 80,
-        "blend_bwd": R * (4 + 96 + 32 + 80) + N * 60 + T * 12,  # + masks read + accumulator flush
-        "project_bwd": P * (4 + 12 + 12 + 4 + 8 + 16 + 36 + 12 + 12 * M) + V * (80 + 96 + 40 + 12 * K),
+        "blend_bwd": R * (4 + 32) + V * (80 + 80) + N * 60 + T * 12,   # list + masks read; records; accumulator rows
+        "project_bwd": project_bwd,
     }[stage]
 
 
@@ -192,7 +206,9 @@ class Workload:
         # outside the operator boundary -- SURVEY.md 8f "next" rows.)
         self.params = {"xyz": t(sc["means3D"]), "features": t(sc["shs"]), "opacity": t(sc["opacities"]),
                        "scaling": t(sc["scales"]), "rotation": t(sc["rotations"])}
-        self.cams = S.make_cameras(CAM_RING, self.W, self.H)
+        self.doc = CONFIG_DOC[cfg_name]
+        self.ring = self.doc["ring"]
+        self.cams = S.make_cameras(self.ring, self.W, self.H)
         d = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device)
         self.cam_dev = [dict(view=d(c.viewmatrix), proj=d(c.projmatrix), campos=d(c.campos)) for c in self.cams]
         self.bg = torch.zeros(3, device=device)
@@ -233,9 +249,19 @@ class Workload:
         import torch
         self.slot_free[slot].record(torch.cuda.current_stream(self.device))
 
-    def view_ids(self, step: int):
-        base = (step * self.world + self.rank) * self.vps
-        return [(base + i) % CAM_RING for i in range(self.vps)]
+    def view_ids(self, step: int, rank: int = None, world: int = None):
+        """Cameras this rank renders in step `step` (rank / world default to the process's own)."""
+        rank = self.rank if rank is None else rank
+        world = self.world if world is None else world
+        if self.doc["step_views"] is not None:      # strong scaling: the step's views are sharded over the ranks
+            from g4splat_b200.view_parallel import shard_views
+            n = self.doc["step_views"]
+            return [(step * n + i) % self.ring for i in shard_views(n, world, rank)]
+        base = (step * world + rank) * self.vps
+        return [(base + i) % self.ring for i in range(self.vps)]
+
+    def views_per_step_total(self):
+        return self.doc["step_views"] if self.doc["step_views"] is not None else self.vps * self.world
 
     def settings(self, mod, vid: int):
         c, cd = self.cams[vid], self.cam_dev[vid]
@@ -368,7 +394,7 @@ def time_train_iteration(wl: "Workload", mod, fused: bool, views: int, device):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for v in range(views):
-        train_iteration(wl, model, mod, (3 + v) % CAM_RING, gt, fused)
+        train_iteration(wl, model, mod, (3 + v) % wl.ring, gt, fused)
     e1.record()
     torch.cuda.synchronize(device)
     return e0.elapsed_time(e1) / views
@@ -414,6 +440,49 @@ def time_region(fn, device, dist_on):
     return ms, out
 
 
+def allreduce_self_check(wl: "Workload", mod, sync, device, step: int = 5):
+    """N ranks, one step, gradients + statistics brought together by `sync`'s transport  ==  ONE rank looping
+    over the views of all ranks (same kernels, local accumulation), within 1e-4 of each block's largest entry.
+    Run after the timed regions; every rank computes the single-rank loop itself."""
+    import torch
+    import torch.distributed as dist
+    from g4splat_b200.view_parallel import ViewShardedGradSync
+
+    def render(s, vid):
+        color, radii, allmap, means2D = wl.rasterize(mod, vid)
+        torch.autograd.backward([color, allmap], [wl.g_color, wl.g_allmap])
+        s.add_view_stats(means2D.grad, radii)
+
+    sync.zero()
+    for vid in wl.view_ids(step):
+        render(sync, vid)
+    sync.allreduce()
+    torch.cuda.synchronize(device)
+    got = {k: v.detach().clone() for k, v in sync._views.items()}
+    got.update(accum=sync._accum.clone(), denom=sync._denom.clone(), max_radii=sync.max_radii.clone())
+    local = ViewShardedGradSync(wl.params, transport="nccl")   # never all-reduced: a single-rank accumulator
+    local.bind(mod)
+    for r in range(wl.world):
+        for vid in wl.view_ids(step, r, wl.world):
+            render(local, vid)
+    torch.cuda.synchronize(device)
+    want = dict(local._views)
+    want.update(accum=local._accum, denom=local._denom, max_radii=local.max_radii)
+    worst, per = 0.0, {}
+    for k in want:
+        w, g = want[k].double(), got[k].double()
+        err = float((w - g).abs().max() / w.abs().max().clamp_min(1e-30))
+        per[k] = err
+        worst = max(worst, err)
+    t = torch.tensor([worst], device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sync.attach()
+    sync.bind(mod)
+    sync.zero()
+    return {"max_rel_err": float(t.item()), "ok": bool(t.item() <= 1e-4), "tolerance": 1e-4, "per_block": per,
+            "what": f"{wl.world}-rank step vs one rank looping over the same {wl.views_per_step_total()} views"}
+
+
 # ----------------------------------------------------------------------------------- CPU oracle
 def cpu_oracle_step(cfg_name: str = CONFIG, threads: int = 0, views: int = 6):
     """`views` full views (forward + backward) of the workload on the host cores with the oracle port: a
@@ -446,6 +515,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--views", type=int, default=8, help="views per GPU per step")
+    ap.add_argument("--config", default=CONFIG, choices=sorted(CONFIG_DOC), help="BASELINE.json workload (default c2)")
+    ap.add_argument("--transport", default="auto", choices=["auto", "nccl", "multimem", "multimem_red"],
+                    help="N > 1: how the ranks' gradient sums meet (g4splat_b200/view_parallel.py)")
+    ap.add_argument("--math", default="exact", choices=["exact", "fast"],
+                    help="forward blend arithmetic: exact = bit-identical to the reference (default), fast = rcp/ex2.approx")
+    ap.add_argument("--no-check", action="store_true", help="N > 1: skip the N-rank == 1-rank gradient self-check")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-iteration", action="store_true", help="skip the informational whole-iteration timing")
     ap.add_argument("--no-settle", action="store_true", help="profiler runs: only W untimed steps, not a pass over the camera ring")
@@ -494,17 +569,20 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=device)
 
-    from g4splat_b200 import _lib
-    from g4splat_b200.view_parallel import ViewShardedGradSync
+    from g4splat_b200.view_parallel import ViewShardedGradSync   # plain torch until told otherwise: loads no native library
     if args.impl == "reference":
+        # nothing of this repository's native code may be mapped in this arm: the statistics pass of the step
+        # loop runs as the reference's own torch expressions (use_native=False below)
         mod = ref_mod
         lib = None
     else:
+        from g4splat_b200 import _lib
         import g4splat_b200.diff_surfel_rasterization as mod
         lib = _lib.load()
+        mod.set_fast_math(args.math == "fast")
 
-    wl = Workload(device, args.views, rank, world)
-    sync = ViewShardedGradSync(wl.params)
+    wl = Workload(device, args.views, rank, world, args.config)
+    sync = ViewShardedGradSync(wl.params, transport=args.transport if dist_on else "nccl", use_native=lib is not None)
     sync.bind(mod)  # B200 operator: kernel-side accumulation into the flat buffer; no-op for the reference
     P, N = wl.P, wl.W * wl.H
     T = ((wl.W + 15) // 16) * ((wl.H + 15) // 16)
@@ -514,7 +592,8 @@ def main():
     # the 64 views need (the instance capacity is sticky and grows with the largest view seen) has been through
     # the caching allocator before the clock starts -- a first-time cudaMalloc of a 100-200 MB block inside the
     # timed region costs 10-100 ms on these hosts (profiles/r01u_bench_stability.md).
-    settle = warmup if args.no_settle else max(warmup, -(-CAM_RING // (args.views * world)))
+    views_total = wl.views_per_step_total()
+    settle = warmup if args.no_settle else max(warmup, -(-wl.ring // views_total))
     run_steps(wl, mod, sync, settle, 0, e2e=False)
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -539,13 +618,13 @@ def main():
         for i in range(n_st):
             nm = lib.g4s_profile_stage_name(i).decode()
             stage_ms[nm], stage_n[nm] = float(buf[i]), int(cnt[i])
-    value = P * args.views * world * args.steps / (ms * 1e-3)
+    value = P * views_total * args.steps / (ms * 1e-3)
 
     # ---- end to end from host buffers ("e2e") ---------------------------------------------------
     run_steps(wl, mod, sync, max(2, settle), 1000, e2e=True)
     ms_e2e, _ = time_region(lambda: run_steps(wl, mod, sync, args.steps, 1000 + max(2, settle), e2e=True), device, dist_on)
-    e2e_value = P * args.views * world * args.steps / (ms_e2e * 1e-3)
-    h2d = args.views * (3 * N)          # one uint8 image per view
+    e2e_value = P * views_total * args.steps / (ms_e2e * 1e-3)
+    h2d = len(wl.view_ids(0)) * (3 * N)   # one uint8 image per view of this rank
     d2h = 4                             # the scalar loss
 
     train_it = None
@@ -561,39 +640,53 @@ def main():
                     "arm": "this repository's fused kernels for every row" if fused else
                            "the reference rasterizer with the reference's torch operator sequences around it"}
 
+    check = None
+    if dist_on and lib is not None and not args.no_check:
+        check = allreduce_self_check(wl, mod, sync, device)
+
     pair_stats = None
     if lib is not None and rank == 0:
         import g4splat_b200.diff_surfel_rasterization as op_mod
         acc = {}
         vids = list(wl.view_ids(3))
-        for vid in vids:                 # untimed: work counters of the views of one step
+        for vid in vids[:8]:             # untimed: work counters of (up to eight) views of one step
             color = wl.rasterize(mod, vid)[0]
             for k, v in op_mod.debug_pair_stats(color).items():
                 acc[k] = max(acc.get(k, 0), v) if k == "longest_tile_list" else acc.get(k, 0) + v
             del color
-        pair_stats = {k: (v if k == "longest_tile_list" else v / len(vids)) for k, v in acc.items()}
+        pair_stats = {k: (v if k == "longest_tile_list" else v / len(vids[:8])) for k, v in acc.items()}
         sync.zero()
 
     if rank != 0:
         if dist_on:
+            sync.close()
             dist.destroy_process_group()
         return 0
 
     peak, peak_src = load_peaks()
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world if args.impl != "reference" else args.gpus,
             "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"c2: 1.0M surfels, SH degree 3, 1920x1080, {args.views} views/GPU/step from a ring of "
-                                   f"{CAM_RING} cameras, fwd+bwd{' + 1 NCCL all-reduce of [P,60] grads' if world > 1 else ''}",
-                       "P": P, "width": wl.W, "height": wl.H, "views_per_gpu_per_step": args.views,
-                       "l2_policy": "inputs larger than L2: 232 MB of parameters + 192 MB of SH gradients per view, a different camera every view",
+            "scaling": wl.doc["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{wl.doc['name']}, " +
+                                   (f"{views_total} views/step sharded over {world} GPU(s)" if wl.doc["step_views"] is not None else
+                                    f"{args.views} views/GPU/step") + f" from a ring of {wl.ring} cameras, fwd+bwd" +
+                                   (f" + gradient sum over ranks ({sync.transport})" if world > 1 else ""),
+                       "P": P, "width": wl.W, "height": wl.H, "views_per_step": views_total,
+                       "views_per_gpu_per_step": len(wl.view_ids(0)),
+                       "l2_policy": f"inputs larger than L2: {232 * P // 1_000_000} MB of parameters + {192 * P // 1_000_000} MB of SH gradients per view, a different camera every view",
                        "untimed_steps_before_timing": settle + 1,
+                       "math": args.math if args.impl != "reference" else "reference",
+                       "transport": sync.transport if world > 1 else None,
                        "parallelism": f"view-sharded dp{world}"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clk}
     if train_it is not None:
         line["train_iteration"] = train_it
+    if check is not None:
+        line["allreduce_check"] = check
+    if world > 1:
+        line["grad_sum"] = {"transport": sync.transport, "bytes_per_rank_per_step": sync.bytes_per_step}
     if args.impl == "reference":
         line["impl"] = "reference"
         line["gpu_launches"] = None
@@ -608,14 +701,18 @@ def main():
         if dom is not None:
             ab = algorithmic_bytes(dom, P, V, R, N, T, Kc, M)
             achieved = ab / (stage_ms[dom] * 1e-3) / 1e9
-            traffic = None
+            # traffic: dram bytes per launch from the committed `ncu --set full` capture of this workload (c2 only),
+            # labelled with the capture it came from -- it is not re-measured by this run
+            traffic, traffic_src = None, None
             tp = ROOT / "profiles" / "traffic.json"
-            if tp.exists():
-                traffic = json.loads(tp.read_text()).get(dom)
+            if tp.exists() and args.config == "c2":
+                tj = json.loads(tp.read_text())
+                traffic, traffic_src = tj.get(dom), tj.get("_source")
             line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                                "peak_source": peak_src,
                                 "algorithmic_bytes_per_launch": ab, "kernel_ms": stage_ms[dom],
-                                "note": "blend kernels are FP32-issue bound, not HBM bound (DESIGN.md); see stages/path"}
+                                "note": "the blend kernels are bound by the FP32 pipe and shared-memory bandwidth, not by HBM (DESIGN.md); see stages/path"}
         per_view_ms = sum(v for v in stage_ms.values() if v > 0)
         line["stages"] = {k: {"ms": stage_ms[k], "launches": stage_n[k],
                               "alg_GBps": (algorithmic_bytes(k, P, V, R, N, T, Kc, M) / (stage_ms[k] * 1e-3) / 1e9) if stage_ms[k] > 0 else None}
@@ -623,7 +720,7 @@ def main():
         pb = path_bytes(P, V, R, N, Kc, M)
         line["path"] = {"alg_bytes_per_view": pb, "kernel_ms_per_view": per_view_ms, "visible": V, "num_rendered": R,
                         "hbm_frac_of_kernel_time": (pb / (per_view_ms * 1e-3) / 1e9 / peak) if per_view_ms > 0 else None,
-                        "hbm_frac_of_step_time": pb * args.views / (ms / args.steps * 1e-3) / 1e9 / peak}
+                        "hbm_frac_of_step_time": pb * len(wl.view_ids(0)) / (ms / args.steps * 1e-3) / 1e9 / peak}
         if pair_stats is not None and stage_ms.get("blend_fwd", 0) > 0 and stage_ms.get("blend_bwd", 0) > 0:
             # secondary roofline: algorithmic ~60 flop per blended pair forward, ~200 backward,
             # against the fp32 SIMT peak 148 SMs x 128 lanes x 2 flop x SM clock under load
@@ -639,16 +736,18 @@ def main():
                               "frac_of_fp32_peak": 200 * pb_ / bwd_s / fp32_peak,
                               "lane_utilisation": pb_ / pe_ if pe_ else None},
                 "lane_slots_skipped_by_culling": 1.0 - pe_ / pair_stats["pair_slots"] if pair_stats["pair_slots"] else None}
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and args.config == "c2":
             v, cores, dt, nv = cpu_oracle_step()
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{nv} views forward+backward at full c2 size, {dt:.1f} s"}
-    print(json.dumps(line))
+    sys.stdout.write("\n" + json.dumps(line) + "\n")   # own line even when a library wrote to stdout before (NCCL banner)
+    sys.stdout.flush()
     dump_trace()
     if os.environ.get("G4S_HOST_TRACE") == "1" and args.impl != "reference":
         import g4splat_b200.diff_surfel_rasterization as op_mod
         sys.stderr.write("host trace (all calls of this process): " + json.dumps(op_mod.host_trace_summary()) + "\n")
     if dist_on:
+        sync.close()
         dist.destroy_process_group()
     return 0
 

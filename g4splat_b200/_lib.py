@@ -33,8 +33,14 @@ SIGNATURES = {
                               _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i]),
     "g4s_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
     "g4s_densify_stats": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "g4s_densify_stats_multimem": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4s_photometric_forward": (_i, [_i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp]),
     "g4s_photometric_backward": (_i, [_i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp]),
+    "g4s_multimem_allreduce": (_i, [_vp, _i64, _vp, _i64, _i, _i, _vp]),
+    "g4s_normal2curv_forward": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "g4s_normal2curv_backward": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "g4s_depth_order_forward": (_i, [_i, _i, _vp, _vp, _vp, _f, _i, _i, _f, _vp, _vp, _vp]),
+    "g4s_depth_order_backward": (_i, [_i, _i, _vp, _vp, _vp, _f, _i, _i, _f, _vp, _vp, _f, _vp, _vp]),
     "g4s_mip_filter": (_i, [_i, _vp, _i, _vp, _f, _f, _f, _vp, _vp, _vp]),
     "g4s_profile_enable": (_i, [_i]),
     "g4s_profile_num_stages": (_i, []),

@@ -384,6 +384,15 @@ int g4s_densify_stats_multimem(int P, const float* dL_dmeans2D, const int* radii
     return densify_stats_impl(P, dL_dmeans2D, radii, accum_mc, denom_mc, max_radii_mc, 1, stream);
 }
 
+int g4s_multimem_allreduce(float* sum_mc, int64_t n_floats, int* max_mc, int64_t n_ints, int rank, int world, void* stream) {
+    if (n_floats < 0 || n_ints < 0 || world < 1 || rank < 0 || rank >= world || (n_floats & 3))
+        return fail(G4S_EINVAL, "g4s_multimem_allreduce: bad sizes (n_floats must be a multiple of 4)");
+    if ((n_floats && !sum_mc) || (n_ints && !max_mc)) return fail(G4S_EINVAL, "g4s_multimem_allreduce: null buffer");
+    if ((reinterpret_cast<uintptr_t>(sum_mc) & 15) != 0) return fail(G4S_EINVAL, "g4s_multimem_allreduce: sum_mc must be 16-byte aligned");
+    launch_multimem_allreduce(sum_mc, (size_t)n_floats, max_mc, (size_t)n_ints, rank, world, (cudaStream_t)stream);
+    return stage_check(false, (cudaStream_t)stream, "multimem_allreduce");
+}
+
 int g4s_photometric_forward(int W, int H, int C, const float* image, const float* gt, const float* window11,
                             float lambda_dssim, double* sums, float* dmaps, float* out3, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
@@ -446,6 +455,46 @@ int g4s_surface_backward(int W, int H, const float* allmap, const float* viewmat
                      dL_dsurf_normal, dL_dsurf_normal_cam, dL_drend_depth, dL_dallmap};
     launch_surface_bwd(a, (cudaStream_t)stream);
     return stage_check(false, (cudaStream_t)stream, "surface_bwd");
+}
+
+int g4s_normal2curv_forward(int W, int H, const float* normal, const float* mask, float* curv, float* sign_map, void* stream) {
+    if (W < 0 || H < 0 || H > 65535) return fail(G4S_EINVAL, "g4s_normal2curv_forward: bad image size");
+    if (W == 0 || H == 0) return G4S_OK;
+    if (!normal || !curv) return fail(G4S_EINVAL, "g4s_normal2curv_forward: null buffer");
+    launch_normal2curv_fwd(W, H, normal, mask, curv, sign_map, (cudaStream_t)stream);
+    return stage_check(false, (cudaStream_t)stream, "normal2curv_fwd");
+}
+int g4s_normal2curv_backward(int W, int H, const float* mask, const float* sign_map, const float* dL_dcurv, float* dL_dnormal,
+                             void* stream) {
+    if (W < 0 || H < 0 || H > 65535) return fail(G4S_EINVAL, "g4s_normal2curv_backward: bad image size");
+    if (W == 0 || H == 0) return G4S_OK;
+    if (!sign_map || !dL_dcurv || !dL_dnormal) return fail(G4S_EINVAL, "g4s_normal2curv_backward: null buffer");
+    launch_normal2curv_bwd(W, H, mask, sign_map, dL_dcurv, dL_dnormal, (cudaStream_t)stream);
+    return stage_check(false, (cudaStream_t)stream, "normal2curv_bwd");
+}
+int g4s_depth_order_forward(int W, int H, const float* depth, const float* prior_depth, const int64_t* pixel_shifts,
+                            float scene_extent, int normalize_loss, int log_space, float log_scale, float* per_pixel,
+                            double* sum, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (W <= 0 || H <= 0 || (int64_t)W * H > 0x7fffffff) return fail(G4S_EINVAL, "g4s_depth_order_forward: bad image size");
+    if (!depth || !prior_depth || !pixel_shifts || (!per_pixel && !sum)) return fail(G4S_EINVAL, "g4s_depth_order_forward: null buffer");
+    int rc;
+    if (sum && (rc = check_cuda(cudaMemsetAsync(sum, 0, sizeof(double), s), "memset depth-order sum"))) return rc;
+    launch_depth_order_fwd(W, H, depth, prior_depth, (const long long*)pixel_shifts, 1.0f / scene_extent, normalize_loss, log_space,
+                           log_scale, per_pixel, sum, s);
+    return stage_check(false, s, "depth_order_fwd");
+}
+int g4s_depth_order_backward(int W, int H, const float* depth, const float* prior_depth, const int64_t* pixel_shifts,
+                             float scene_extent, int normalize_loss, int log_space, float log_scale, const float* dL_dper_pixel,
+                             const float* dL_dloss, float scale, float* dL_ddepth, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (W <= 0 || H <= 0 || (int64_t)W * H > 0x7fffffff) return fail(G4S_EINVAL, "g4s_depth_order_backward: bad image size");
+    if (!depth || !prior_depth || !pixel_shifts || !dL_ddepth) return fail(G4S_EINVAL, "g4s_depth_order_backward: null buffer");
+    int rc;
+    if ((rc = check_cuda(cudaMemsetAsync(dL_ddepth, 0, sizeof(float) * (size_t)W * H, s), "memset dL_ddepth"))) return rc;
+    launch_depth_order_bwd(W, H, depth, prior_depth, (const long long*)pixel_shifts, 1.0f / scene_extent, normalize_loss, log_space,
+                           log_scale, dL_dper_pixel, dL_dloss, scale, dL_ddepth, s);
+    return stage_check(false, s, "depth_order_bwd");
 }
 
 // ---- introspection ---------------------------------------------------------------------------

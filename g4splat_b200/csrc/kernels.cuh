@@ -108,6 +108,7 @@ void launch_acc_clear(int P, const int* radii, float4* acc, cudaStream_t s);
 
 void launch_densify_stats(int P, const float* dL_dmeans2D, const int* radii, float* accum, float* denom,
                           int* max_radii, int multimem, cudaStream_t s);
+void launch_multimem_allreduce(float* mc, size_t n_floats, int* mc_max, size_t n_ints, int rank, int world, cudaStream_t s);
 void launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s);
 
 // ---- compute_mip_filter (gaussian_model.cu) ---------------------------------------------------
@@ -119,6 +120,15 @@ void launch_photometric_fwd(int W, int H, int C, const float* img, const float* 
                             double* sums, float* dmaps, float* out3, cudaStream_t s);
 void launch_photometric_bwd(int W, int H, int C, const float* img, const float* gt, const float* window11, float lambda,
                             const float* dmaps, const float* dL_dloss, float* dL_dimg, cudaStream_t s);
+
+// ---- image-space regularisers (regularizers.cu) -------------------------------------------------
+void launch_normal2curv_fwd(int W, int H, const float* normal, const float* mask, float* curv, float* sg, cudaStream_t s);
+void launch_normal2curv_bwd(int W, int H, const float* mask, const float* sg, const float* g_curv, float* g_normal, cudaStream_t s);
+void launch_depth_order_fwd(int W, int H, const float* depth, const float* prior, const long long* shifts, float inv_extent,
+                            int normalize, int log_space, float log_scale, float* per_pixel, double* sum, cudaStream_t s);
+void launch_depth_order_bwd(int W, int H, const float* depth, const float* prior, const long long* shifts, float inv_extent,
+                            int normalize, int log_space, float log_scale, const float* g, const float* g_scalar, float scale,
+                            float* g_depth, cudaStream_t s);
 
 // ---- render() post-processing (surface.cu) ----------------------------------------------------
 struct SurfaceFwdArgs {

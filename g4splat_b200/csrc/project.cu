@@ -838,6 +838,41 @@ __global__ void __launch_bounds__(256) densify_stats_kernel(int P, const float* 
     }
 }
 
+// ---- NVLS all-reduce of the view-sharded gradient buffer (view_parallel, transport "multimem") -----------------
+// Every rank holds its own partial sums in a buffer that all ranks map at the same offset of one NVSwitch multicast
+// object.  Rank r owns the r-th slice of the buffer: one multimem.ld_reduce pulls the slice's 16 bytes from EVERY
+// rank and adds them inside the switch, one multimem.st pushes the sum back into every rank's replica -- each byte
+// crosses each link once per direction (a ring all-reduce moves 2 (N-1)/N of the buffer in N-1 dependent hops).
+// The int32 block behind the floats (max_radii2D) is combined with max instead of add.  The caller brackets the
+// kernel with barriers (all partial sums complete before, all slices written after).
+__global__ void __launch_bounds__(512) multimem_allreduce_kernel(float* mc, size_t n_add_quads, size_t q_begin, size_t q_end,
+                                                                int* mc_max, size_t m_begin, size_t m_end) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t q = q_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < q_end; q += stride) {
+        float4 v;
+        float* p = mc + 4 * q;
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                     ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    }
+    (void)n_add_quads;
+    for (size_t i = m_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m_end; i += stride) {
+        int v;
+        int* p = mc_max + i;
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.max.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        asm volatile("multimem.st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    }
+}
+void launch_multimem_allreduce(float* mc, size_t n_floats, int* mc_max, size_t n_ints, int rank, int world, cudaStream_t s) {
+    const size_t quads = n_floats / 4;
+    const size_t qb = quads * rank / world, qe = quads * (rank + 1) / world;
+    const size_t mb = n_ints * rank / world, me = n_ints * (rank + 1) / world;
+    if (qe == qb && me == mb) return;
+    multimem_allreduce_kernel<<<148 * 4, 512, 0, s>>>(mc, quads, qb, qe, mc_max, mb, me);
+    count_launch();
+}
+
 // Zero the blend-stage accumulator rows of the visible Gaussians only (the others are never read):
 // 4 B read per Gaussian + 80 B written per visible one, instead of an 80 P byte memset.
 __global__ void __launch_bounds__(256) acc_clear_kernel(int P, const int* __restrict__ radii, float4* __restrict__ acc) {

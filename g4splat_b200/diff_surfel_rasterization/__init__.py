@@ -22,6 +22,8 @@ then reported by the next call).
 from __future__ import annotations
 
 import os
+import threading
+import weakref
 from typing import NamedTuple, Optional
 
 import torch
@@ -83,7 +85,7 @@ class _CapacityPolicy:
             self.cap[dev] = want
 
 
-_capacity = _CapacityPolicy()
+_capacity = _CapacityPolicy()   # keyed by device index inside
 # G4S_HOST_TRACE=1: wall-clock of the host-side segments of every call (diagnostics; host_trace_summary())
 _HOST_TRACE = os.environ.get("G4S_HOST_TRACE") == "1"
 _host_times = {"fwd_launch": [], "fwd_wait": [], "bwd": []}
@@ -93,68 +95,179 @@ def host_trace_summary() -> dict:
     import statistics
     return {k: dict(n=len(v), mean_us=1e6 * statistics.fmean(v), p50_us=1e6 * statistics.median(v), max_us=1e6 * max(v))
             for k, v in _host_times.items() if v}
-# (num_rendered, longest tile list, visible Gaussians) of the most recent forward whose plan the
-# host has waited for; benchmarks read it to size the algorithmic-bytes model
-last_counts = {"num_rendered": 0, "max_tile_list": 0, "visible": 0}
-_pending_overflow = []  # (event, pinned counts, capacity) of G4S_SYNC=none calls not yet checked
-_RING = 256             # pinned count slots; a slot is reused only after _RING further forwards
-_ring = None
-_ring_next = 0
+
+
+_RING = 256             # pinned count slots per device; a slot is reused only after _RING further forwards
+
+
+class _DeviceState:
+    """Everything the shim remembers between calls, per CUDA device (one process may drive several devices
+    from several threads): the pinned ring the plan stage reports its counts into, the overflow checks a
+    G4S_SYNC=none caller still owes, and the counts of the most recent forward the host has waited for."""
+
+    def __init__(self):
+        self.lock = threading.Lock()
+        self.ring = None
+        self.ring_next = 0
+        self.pending_overflow = []   # (event, pinned counts, capacity) of G4S_SYNC=none calls not yet checked
+        self.last_counts = {"num_rendered": 0, "max_tile_list": 0, "visible": 0}
+
+
+_states = {}
+_states_lock = threading.Lock()
+
+
+def _state(dev: torch.device) -> _DeviceState:
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    st = _states.get(idx)
+    if st is None:
+        with _states_lock:
+            st = _states.setdefault(idx, _DeviceState())
+    return st
+
+
+class _LastCounts(dict):
+    """(num_rendered, longest tile list, visible Gaussians) of the most recent forward on the CURRENT device
+    whose plan the host has waited for; benchmarks read it to size the algorithmic-bytes model."""
+
+    def _d(self):
+        return _state(torch.device("cuda", torch.cuda.current_device())).last_counts
+
+    def __getitem__(self, k):
+        return self._d()[k]
+
+    def __iter__(self):
+        return iter(self._d())
+
+    def __len__(self):
+        return len(self._d())
+
+    def keys(self):
+        return self._d().keys()
+
+    def items(self):
+        return self._d().items()
+
+    def __repr__(self):
+        return repr(self._d())
+
+
+last_counts = _LastCounts()
 
 
 def _sync_mode() -> str:
     return os.environ.get("G4S_SYNC", "plan")
 
 
-def _pinned_counts() -> torch.Tensor:
-    """int32[4] view into a pinned ring (cudaHostAlloc per call would serialise the device)."""
-    global _ring, _ring_next
-    if _ring is None:
-        _ring = torch.zeros((_RING, 4), dtype=torch.int32).pin_memory()
-    slot = _ring[_ring_next]
-    _ring_next = (_ring_next + 1) % _RING
-    if _ring_next == 0 and _pending_overflow:
+def _pinned_counts(st: _DeviceState) -> torch.Tensor:
+    """int32[4] view into the device's pinned ring (cudaHostAlloc per call would serialise the device)."""
+    with st.lock:
+        if st.ring is None:
+            st.ring = torch.zeros((_RING, 4), dtype=torch.int32).pin_memory()
+        slot = st.ring[st.ring_next]
+        st.ring_next = (st.ring_next + 1) % _RING
+        wrapped = st.ring_next == 0
+    if wrapped and st.pending_overflow:
         torch.cuda.synchronize()
-        _check_pending()
+        _check_pending(st)
     return slot
 
 
-def _check_pending() -> None:
+def _check_pending(st: _DeviceState, dev_index: int = None, wait: bool = False) -> None:
+    """Capacity checks owed by G4S_SYNC=none forwards: raise if one of them overflowed its binning buffer
+    (its kernels were no-ops), and feed the observed counts back into the capacity policy."""
     still = []
-    for ev, counts, cap in _pending_overflow:
+    for ev, counts, cap in st.pending_overflow:
+        if wait:
+            ev.synchronize()
         if ev.query():
-            if int(counts[0]) > cap:
-                _pending_overflow.clear()
+            n = int(counts[0])
+            if dev_index is not None:
+                _capacity.observe(dev_index, n)
+            st.last_counts.update(num_rendered=n, max_tile_list=int(counts[1]), visible=int(counts[2]))
+            if n > cap:
+                st.pending_overflow.clear()
                 raise RuntimeError(
-                    f"g4s rasterizer: a previous G4S_SYNC=none forward needed {int(counts[0])} instances "
+                    f"g4s rasterizer: a previous G4S_SYNC=none forward needed {n} instances "
                     f"but was given capacity {cap}; its outputs are invalid")
         else:
             still.append((ev, counts, cap))
-    _pending_overflow[:] = still
+    st.pending_overflow[:] = still
+
+
+def set_fast_math(on: bool) -> bool:
+    """Arithmetic of the forward blend (g4s_set_fast_math): False (default) = IEEE division / expf, results
+    bit-identical to the reference; True = rcp.approx / ex2.approx, values within 1e-5, threshold decisions
+    may flip within an ulp of alpha = 1/255, T = 1e-4, T = 0.5.  Returns the previous setting."""
+    return bool(_LIB.g4s_set_fast_math(int(bool(on))))
+
+
+if os.environ.get("G4S_MATH") == "fast":
+    set_fast_math(True)
 
 
 # ---- opt-in gradient sink (extension; the reference API is unchanged when it is not used) --------
-# Maps the data_ptr of a leaf parameter tensor to the buffer its gradient is accumulated in.  When
-# an input of the operator IS such a parameter, backward adds that view's gradient straight into
-# the buffer inside the kernel (visible rows only) and returns None for it, instead of returning a
-# dense tensor that autograd then adds to `.grad` (view_parallel.ViewShardedGradSync.bind()).
-_grad_sink = {}
+# Maps a leaf parameter tensor to the buffer its gradient is accumulated in.  When an input of the
+# operator IS such a parameter, backward adds that view's gradient straight into the buffer inside
+# the kernel (visible rows only) and returns None for it, instead of returning a dense tensor that
+# autograd then adds to `.grad` (view_parallel.ViewShardedGradSync.bind()).  Entries hold a weak
+# reference to their parameter: a tensor that merely reuses the address of a replaced parameter
+# (densification, optimizer re-creation) never matches, and dead entries are dropped.
 _ACC_BITS = {"means3D": 1, "sh": 2, "opacities": 4, "scales": 8, "rotations": 16}
+_ACC_MULTIMEM = 32
 
 
-def set_gradient_sink(mapping) -> None:
-    """mapping: {parameter tensor: accumulation buffer of the same shape} (empty / None clears it)."""
+class _Sink:
+    __slots__ = ("ref", "buf", "ptr", "multimem")
+
+    def __init__(self, param, buf, ptr, multimem):
+        self.ref, self.buf, self.ptr, self.multimem = weakref.ref(param), buf, ptr, multimem
+
+
+_grad_sink = {}
+
+
+def set_gradient_sink(mapping, multicast=None) -> None:
+    """mapping: {parameter tensor: accumulation buffer of the same shape} (empty / None clears it).
+    multicast: optional {parameter tensor: int} -- the NVSwitch multicast address that maps the parameter's
+    accumulation buffer on every rank; the kernels then add with multimem.red (all ranks' buffers receive the
+    gradient, include/g4s_rasterizer.h G4S_ACC_MULTIMEM).  Either every entry has one or none has."""
     _grad_sink.clear()
-    for param, buf in (mapping or {}).items():
+    multicast = multicast or {}
+    items = list((mapping or {}).items())
+    if multicast and len(multicast) != len(items):
+        raise ValueError("set_gradient_sink: give a multicast address for every parameter or for none")
+    for param, buf in items:
         if buf.shape != param.shape or buf.dtype != torch.float32 or not buf.is_contiguous():
             raise ValueError("gradient sink buffers must be contiguous float32 tensors shaped like their parameter")
-        _grad_sink[(param.data_ptr(), tuple(param.shape))] = buf
+        if buf.data_ptr() % 4 != 0:
+            raise ValueError("gradient sink buffers must be 4-byte aligned")
+        mc = multicast.get(param)
+        if mc is not None and int(mc) % 16 != buf.data_ptr() % 16:
+            raise ValueError("multicast address and local buffer must share their 16-byte alignment")
+        _grad_sink[id(param)] = _Sink(param, buf, int(mc) if mc is not None else buf.data_ptr(), mc is not None)
 
 
 def _sink_for(t: torch.Tensor):
     if not _grad_sink or t is None or t.numel() == 0 or not t.requires_grad or not t.is_leaf:
         return None
-    return _grad_sink.get((t.data_ptr(), tuple(t.shape)))
+    s = _grad_sink.get(id(t))
+    if s is None:
+        return None
+    if s.ref() is not t:      # the parameter died and its id was reused
+        del _grad_sink[id(t)]
+        return None
+    return s
+
+
+def _dump_snapshot(name: str, args) -> None:
+    """debug=True: what the reference does when a call throws (RAST/diff_surfel_rasterization/__init__.py:83-90,
+    133-140): the arguments, copied to the CPU before the call, are written next to the script."""
+    torch.save(args, name)
+
+
+def _cpu_copy(args):
+    return tuple(a.cpu().clone() if isinstance(a, torch.Tensor) else a for a in args)
 
 
 def _plan_and_render(dev, P, W, H, bg, rs, plan):
@@ -163,6 +276,8 @@ def _plan_and_render(dev, P, W, H, bg, rs, plan):
     Returns (color, others, radii, geom, binning, img, capacity, num_rendered, pinned counts)."""
     debug = bool(rs.debug)
     f32 = dict(dtype=torch.float32, device=dev)
+    st = _state(dev)
+    dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
     if _HOST_TRACE:
         import time
         t_begin = time.perf_counter()
@@ -174,14 +289,14 @@ def _plan_and_render(dev, P, W, H, bg, rs, plan):
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
         geom = torch.empty((_LIB.g4s_geom_bytes(P),), dtype=torch.uint8, device=dev)
         img = torch.empty((_LIB.g4s_image_bytes(W, H),), dtype=torch.uint8, device=dev)
-        counts = _pinned_counts()
+        counts = _pinned_counts(st)
         mode = _sync_mode()
         if mode == "none":
-            _check_pending()
+            _check_pending(st, dev_index)
         _lib.check(plan(radii, geom, img, counts, sp))
         planned = torch.cuda.Event()
         planned.record(stream)
-        cap = _capacity.guess(dev.index or 0, P)
+        cap = _capacity.guess(dev_index, P)
         while True:
             binning = torch.empty((_LIB.g4s_binning_bytes(cap),), dtype=torch.uint8, device=dev)
             if debug:
@@ -193,7 +308,7 @@ def _plan_and_render(dev, P, W, H, bg, rs, plan):
                 P, W, H, bg.data_ptr(), geom.data_ptr(), img.data_ptr(), binning.data_ptr(), cap,
                 color.data_ptr(), others.data_ptr(), sp, int(debug)))
             if mode == "none":
-                _pending_overflow.append((planned, counts, cap))
+                st.pending_overflow.append((planned, counts, cap))
                 num_rendered = -1
                 break
             if _HOST_TRACE:
@@ -204,14 +319,40 @@ def _plan_and_render(dev, P, W, H, bg, rs, plan):
                 _host_times["fwd_launch"].append(t_wait - t_begin)
                 _host_times["fwd_wait"].append(t_done - t_wait)
             num_rendered = int(counts[0])
-            last_counts.update(num_rendered=num_rendered, max_tile_list=int(counts[1]), visible=int(counts[2]))
-            _capacity.observe(dev.index or 0, num_rendered)
+            st.last_counts.update(num_rendered=num_rendered, max_tile_list=int(counts[1]), visible=int(counts[2]))
+            _capacity.observe(dev_index, num_rendered)
             if num_rendered <= cap:
                 break
             cap = _capacity.bucket(num_rendered + 65536)  # the speculative launch was a no-op: re-issue
         if debug and rs.prefiltered and int(counts[3]) != 0:
             raise RuntimeError("Point is filtered although prefiltered is set. This shouldn't happen!")
     return color, others, radii, geom, binning, img, cap, num_rendered, counts
+
+
+def _settle_pending(dev) -> None:
+    """G4S_SYNC=none: before a backward replays a forward, wait for the capacity checks that are still owed
+    (a forward that overflowed was a no-op and left its outputs and masks unwritten; the backward kernels
+    refuse to run on it too, but the caller must hear about it now, not one call late)."""
+    st = _state(dev)
+    if st.pending_overflow:
+        _check_pending(st, dev.index if dev.index is not None else torch.cuda.current_device(), wait=True)
+
+
+def _resolve_sinks(named):
+    """named: {kernel output name: operator input}.  Returns ({name: _Sink}, ACC_MULTIMEM or 0)."""
+    if not _grad_sink:
+        return None, 0
+    out = {}
+    for k, t in named.items():
+        s = _sink_for(t)
+        if s is not None:
+            out[k] = s
+    if not out:
+        return None, 0
+    mm = {s.multimem for s in out.values()}
+    if len(mm) != 1:
+        raise RuntimeError("gradient sinks of one call must all be multicast or all local")
+    return out, (_ACC_MULTIMEM if mm.pop() else 0)
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
@@ -261,11 +402,23 @@ class _RasterizeGaussians(torch.autograd.Function):
                     _ptr(view), _ptr(proj), _ptr(campos), float(rs.tanfovx), float(rs.tanfovy),
                     int(bool(rs.prefiltered)), radii.data_ptr(), geom.data_ptr(), img.data_ptr(),
                     counts.data_ptr(), sp, int(debug))
-            color, others, radii, geom, binning, img, cap, num_rendered, counts = _plan_and_render(dev, P, W, H, bg, rs, plan)
+            if debug:
+                # reference :83-90 -- arguments copied before the call so that a failure can be replayed
+                cpu_args = _cpu_copy((rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier,
+                                      cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height,
+                                      rs.image_width, sh, rs.sh_degree, rs.campos, rs.prefiltered, rs.debug))
+                try:
+                    color, others, radii, geom, binning, img, cap, num_rendered, counts = _plan_and_render(dev, P, W, H, bg, rs, plan)
+                except Exception as ex:
+                    _dump_snapshot("snapshot_fw.dump", cpu_args)
+                    print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                    raise ex
+            else:
+                color, others, radii, geom, binning, img, cap, num_rendered, counts = _plan_and_render(dev, P, W, H, bg, rs, plan)
             ctx.counts = counts
 
-        ctx.sinks = {"means3D": _sink_for(means3D), "sh": _sink_for(sh), "opacities": _sink_for(opacities),
-                     "scales": _sink_for(scales), "rotations": _sink_for(rotations)} if _grad_sink else None
+        ctx.sinks, ctx.sink_flags = _resolve_sinks({"means3D": means3D, "sh": sh, "opacities": opacities,
+                                                    "scales": scales, "rotations": rotations})
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
         ctx.M = M
@@ -282,6 +435,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         rs = ctx.raster_settings
         colors_c, means3D_c, scales_c, rots_c, cov_c, radii, sh_c, geom, binning, img = ctx.saved_tensors
         dev = means3D_c.device
+        _settle_pending(dev)
         P = int(means3D_c.size(0))
         M = ctx.M
         H, W = int(rs.image_height), int(rs.image_width)
@@ -291,14 +445,14 @@ class _RasterizeGaussians(torch.autograd.Function):
         acc_mask = 0
 
         def out(name, shape):
-            """(tensor handed to the kernel, tensor returned to autograd)"""
+            """(device address handed to the kernel, tensor returned to autograd)"""
             nonlocal acc_mask
-            buf = sinks.get(name) if P != 0 else None
-            if buf is not None:
-                acc_mask |= _ACC_BITS[name]
-                return buf, None
+            sink = sinks.get(name) if P != 0 else None
+            if sink is not None:
+                acc_mask |= _ACC_BITS[name] | ctx.sink_flags
+                return sink.ptr, None
             t = alloc(shape, **f32)
-            return t, t
+            return _ptr(t), t
 
         k_means3D, dL_dmeans3D = out("means3D", (P, 3))
         k_sh, dL_dsh = out("sh", (P, M, 3))
@@ -321,14 +475,29 @@ class _RasterizeGaussians(torch.autograd.Function):
             with torch.cuda.device(dev):
                 sp = torch.cuda.current_stream(dev).cuda_stream
                 scratch = torch.empty((_LIB.g4s_backward_scratch_bytes(P),), dtype=torch.uint8, device=dev)
-                _lib.check(_LIB.g4s_backward(
-                    P, int(rs.sh_degree), M, W, H, bg.data_ptr(), _ptr(means3D_c), _ptr(sh_c), _ptr(colors_c),
-                    _ptr(scales_c), float(rs.scale_modifier), _ptr(rots_c), _ptr(cov_c), _ptr(view), _ptr(proj),
-                    _ptr(campos), float(rs.tanfovx), float(rs.tanfovy), radii.data_ptr(), geom.data_ptr(),
-                    binning.data_ptr(), int(ctx.capacity), img.data_ptr(), g_color.data_ptr(), g_others.data_ptr(),
-                    k_means3D.data_ptr(), dL_dmeans2D.data_ptr(), _ptr(k_sh), _ptr(dL_dcolors),
-                    k_opacity.data_ptr(), k_scales.data_ptr(), k_rots.data_ptr(),
-                    _ptr(dL_dtransMat), acc_mask, scratch.data_ptr(), sp, int(bool(rs.debug))))
+
+                def call():
+                    _lib.check(_LIB.g4s_backward(
+                        P, int(rs.sh_degree), M, W, H, bg.data_ptr(), _ptr(means3D_c), _ptr(sh_c), _ptr(colors_c),
+                        _ptr(scales_c), float(rs.scale_modifier), _ptr(rots_c), _ptr(cov_c), _ptr(view), _ptr(proj),
+                        _ptr(campos), float(rs.tanfovx), float(rs.tanfovy), radii.data_ptr(), geom.data_ptr(),
+                        binning.data_ptr(), int(ctx.capacity), img.data_ptr(), g_color.data_ptr(), g_others.data_ptr(),
+                        k_means3D, dL_dmeans2D.data_ptr(), k_sh, _ptr(dL_dcolors),
+                        k_opacity, k_scales, k_rots,
+                        _ptr(dL_dtransMat), acc_mask, scratch.data_ptr(), sp, int(bool(rs.debug))))
+                if rs.debug:
+                    # reference :133-140
+                    cpu_args = _cpu_copy((rs.bg, means3D_c, radii, colors_c, scales_c, rots_c, rs.scale_modifier, cov_c,
+                                          rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_out_color, grad_depth,
+                                          sh_c, rs.sh_degree, rs.campos, geom, ctx.num_rendered, binning, img, rs.debug))
+                    try:
+                        call()
+                    except Exception as ex:
+                        _dump_snapshot("snapshot_bw.dump", cpu_args)
+                        print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+                        raise ex
+                else:
+                    call()
         if _HOST_TRACE:
             _host_times["bwd"].append(time.perf_counter() - t_begin)
         # same order as the reference (RAST/diff_surfel_rasterization/__init__.py:144-154)
@@ -394,6 +563,12 @@ class _RasterizeGaussianModel(torch.autograd.Function):
                     geom.data_ptr(), img.data_ptr(), counts.data_ptr(), sp, int(bool(rs.debug)))
             color, others, radii, geom, binning, img, cap, num_rendered, counts = _plan_and_render(dev, P, W, H, bg, rs, plan)
             ctx.counts = counts
+        # the SH gradient is one kernel output mode for both tensors: they are sunk together or not at all
+        ctx.sinks, ctx.sink_flags = _resolve_sinks({"means3D": xyz, "sh": features_dc, "sh_rest": features_rest,
+                                                    "opacities": opacity, "scales": scaling, "rotations": rotation})
+        if ctx.sinks is not None and M > 1 and (("sh" in ctx.sinks) != ("sh_rest" in ctx.sinks)):
+            ctx.sinks.pop("sh", None)
+            ctx.sinks.pop("sh_rest", None)
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
         ctx.M = M
@@ -413,14 +588,25 @@ class _RasterizeGaussianModel(torch.autograd.Function):
         H, W = int(rs.image_height), int(rs.image_width)
         f32 = dict(dtype=torch.float32, device=dev)
         alloc = torch.zeros if P == 0 else torch.empty  # every element is written by the kernels
-        # (the multi-view gradient sink of the operator API is not wired to the raw entry points: acc_mask = 0)
+        _settle_pending(dev)
+        sinks = ctx.sinks or {}
         acc_mask = 0
-        g_xyz = k_xyz = alloc((P, 3), **f32)
-        g_dc = k_dc = alloc((P, 1, 3), **f32)
-        g_rest = k_rest = alloc((P, M - 1, 3), **f32)
-        g_op = k_op = alloc((P, 1), **f32)
-        g_sc = k_sc = alloc((P, 2), **f32)
-        g_rot = k_rot = alloc((P, 4), **f32)
+
+        def out(name, shape, bit):
+            nonlocal acc_mask
+            sink = sinks.get(name) if P != 0 else None
+            if sink is not None:
+                acc_mask |= bit | ctx.sink_flags
+                return sink.ptr, None
+            t = alloc(shape, **f32)
+            return _ptr(t), t
+
+        k_xyz, g_xyz = out("means3D", (P, 3), _ACC_BITS["means3D"])
+        k_dc, g_dc = out("sh", (P, 1, 3), _ACC_BITS["sh"])
+        k_rest, g_rest = out("sh_rest", (P, M - 1, 3), _ACC_BITS["sh"])
+        k_op, g_op = out("opacities", (P, 1), _ACC_BITS["opacities"])
+        k_sc, g_sc = out("scales", (P, 2), _ACC_BITS["scales"])
+        k_rot, g_rot = out("rotations", (P, 4), _ACC_BITS["rotations"])
         g_means2D = alloc((P, 3), **f32)
         if P != 0:
             g_color = _f32c(grad_out_color, "dL_dout_color")
@@ -437,9 +623,9 @@ class _RasterizeGaussianModel(torch.autograd.Function):
                     opac_c.data_ptr(), scal_c.data_ptr(), float(rs.scale_modifier), rot_c.data_ptr(),
                     mip_c.data_ptr() if ctx.has_mip else None, _ptr(view), _ptr(proj), _ptr(campos),
                     float(rs.tanfovx), float(rs.tanfovy), radii.data_ptr(), geom.data_ptr(), binning.data_ptr(),
-                    int(ctx.capacity), img.data_ptr(), g_color.data_ptr(), g_others.data_ptr(), k_xyz.data_ptr(),
-                    g_means2D.data_ptr(), k_dc.data_ptr(), _ptr(k_rest), k_op.data_ptr(), k_sc.data_ptr(),
-                    k_rot.data_ptr(), acc_mask, scratch.data_ptr(), sp, int(bool(rs.debug))))
+                    int(ctx.capacity), img.data_ptr(), g_color.data_ptr(), g_others.data_ptr(), k_xyz,
+                    g_means2D.data_ptr(), k_dc, k_rest, k_op, k_sc,
+                    k_rot, acc_mask, scratch.data_ptr(), sp, int(bool(rs.debug))))
         return g_xyz, g_means2D, g_dc, g_rest, g_op, g_sc, g_rot, None, None
 
 

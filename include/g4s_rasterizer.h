@@ -123,6 +123,12 @@ int g4s_forward_render(int P, int W, int H, const float* background,
 #define G4S_ACC_OPACITY 4
 #define G4S_ACC_SCALES 8
 #define G4S_ACC_ROTATIONS 16
+/* The accumulated outputs are NVSwitch multicast addresses (one buffer per rank mapped at the same offset of
+ * a CUDA multicast object): the kernel adds with multimem.red, so every rank's replica receives this view's
+ * gradient and the per-step all-reduce of the view-sharded trainer needs no data movement of its own
+ * (fused producer + collective).  Requires NVLS-capable hardware; the caller owns the barrier
+ * that orders these reductions before any rank reads its replica. */
+#define G4S_ACC_MULTIMEM 32
 int g4s_backward(int P, int D, int M, int W, int H, const float* background,
                  const float* means3D, const float* shs, const float* colors_precomp,
                  const float* scales, float scale_modifier, const float* rotations,
@@ -180,6 +186,41 @@ int g4s_mark_visible(int P, const float* means3D, const float* viewmatrix, const
  * for radii[i] > 0:  accum[i] += |dL_dmeans2D[i].xy|, denom[i] += 1, max_radii[i] = max(., radii[i]). */
 int g4s_densify_stats(int P, const float* dL_dmeans2D, const int* radii, float* accum, float* denom,
                       int* max_radii, void* stream);
+/* Same pass with accum / denom / max_radii given as NVSwitch MULTICAST addresses of buffers every rank holds
+ * at the same offset (CUDA multicast object, e.g. torch symmetric memory's multicast_ptr): the update of a
+ * visible Gaussian is one multimem.red per value and lands in every rank's replica (G4S_ACC_MULTIMEM above). */
+int g4s_densify_stats_multimem(int P, const float* dL_dmeans2D, const int* radii, float* accum_mc, float* denom_mc,
+                               int* max_radii_mc, void* stream);
+
+/* ---- gradient all-reduce of the view-sharded trainer over NVSwitch multicast ---------------------
+ * sum_mc / max_mc: MULTICAST addresses (CUDA multicast object; torch symmetric memory's multicast_ptr) of an fp32
+ * block of n_floats (multiple of 4, 16-byte aligned) and an int32 block of n_ints that every rank holds at the same
+ * offset.  Rank `rank` of `world` combines its slice of both blocks across all ranks with multimem.ld_reduce (add /
+ * max, inside the switch) and writes the result to every replica with multimem.st.  The caller orders it with a
+ * barrier on either side (all ranks' partial sums complete / all slices written). */
+int g4s_multimem_allreduce(float* sum_mc, int64_t n_floats, int* max_mc, int64_t n_ints, int rank, int world, void* stream);
+
+/* ---- image-space regularisers (the part beside the photometric loss) -------------
+ * normal2curv: matcha/dm_utils/rendering.py:392-406 (2DGS/train_with_refine_depth.py:415):
+ *   curv[1,H,W] = L1 norm over channels of  mask * sum_{up,left,bottom,right} (n_nb - n_c m_c) m_nb, replicate padding.
+ *   normal [3,H,W]; mask [1,H,W] fp32 or NULL (= ones; the trainer passes ones).  sign_map [3,H,W] (optional
+ *   output, required by the backward): sign of each channel's sum times the mask.
+ * depth-order loss: matcha/dm_regularization/depth.py:142-222 (train_with_refine_depth.py:465): every pixel is
+ *   paired with the pixel `pixel_shifts[i]` away (int64 [N,2] = (dy, dx), drawn by the caller exactly as the
+ *   reference draws them, clamped to the image here); loss_i = -min(diff * prior_diff, 0) with both differences
+ *   divided by scene_extent, prior_diff optionally reduced to its sign, optionally log(1 + log_scale * loss_i).
+ *   per_pixel [N] and / or sum (device double[1]) are written.  Backward: dL_dper_pixel [N], or NULL with the
+ *   scalar upstream dL_dloss (device float[1], NULL = 1) times `scale` (1/N for the mean); dL_ddepth [N] is
+ *   fully written. */
+int g4s_normal2curv_forward(int W, int H, const float* normal, const float* mask, float* curv, float* sign_map, void* stream);
+int g4s_normal2curv_backward(int W, int H, const float* mask, const float* sign_map, const float* dL_dcurv, float* dL_dnormal,
+                             void* stream);
+int g4s_depth_order_forward(int W, int H, const float* depth, const float* prior_depth, const int64_t* pixel_shifts,
+                            float scene_extent, int normalize_loss, int log_space, float log_scale, float* per_pixel,
+                            double* sum, void* stream);
+int g4s_depth_order_backward(int W, int H, const float* depth, const float* prior_depth, const int64_t* pixel_shifts,
+                             float scene_extent, int normalize_loss, int log_space, float log_scale, const float* dL_dper_pixel,
+                             const float* dL_dloss, float scale, float* dL_ddepth, void* stream);
 
 /* ---- photometric loss ---------------------------------------------------------
  * Replaces what the trainer does with the rendered image every iteration

@@ -34,10 +34,28 @@ PKG = OUT / "diff_surfel_rasterization"
 OBJ = OUT / "obj"
 SOURCES = ["cuda_rasterizer/rasterizer_impl.cu", "cuda_rasterizer/forward.cu",
            "cuda_rasterizer/backward.cu", "rasterize_points.cu", "ext.cpp"]
+# The reference's own Python call surface around the operator (2d-gaussian-splatting/), installed VERBATIM into
+# oracle/_ref/twodgs/ (git-ignored; ships to the GPU box like the .so) so that GPU tests can run the unmodified
+# render() / GaussianModel / loss code on either operator.  scene/__init__.py (dataset readers) is not needed.
+TWODGS = REF.parent.parent
+TWODGS_OUT = OUT / "twodgs"
+TWODGS_FILES = ["gaussian_renderer/__init__.py", "scene/gaussian_model.py", "scene/cameras.py", "utils/point_utils.py",
+                "utils/sh_utils.py", "utils/general_utils.py", "utils/graphics_utils.py", "utils/loss_utils.py",
+                "utils/system_utils.py"]
 
 
 def reference_available() -> bool:
     return all((REF / s).exists() for s in SOURCES)
+
+
+def install_twodgs() -> bool:
+    """Copy the reference's Python modules (verbatim) next to the extension.  True when they are in place."""
+    if all((TWODGS / f).exists() for f in TWODGS_FILES):
+        for f in TWODGS_FILES:
+            dst = TWODGS_OUT / f
+            dst.parent.mkdir(parents=True, exist_ok=True)
+            shutil.copyfile(TWODGS / f, dst)
+    return all((TWODGS_OUT / f).exists() for f in TWODGS_FILES)
 
 
 def up_to_date() -> bool:
@@ -89,6 +107,7 @@ def build(force: bool = False, verbose: bool = True) -> bool:
     subprocess.run(link, check=True)
     # "install" step: the reference's own Python wrapper, verbatim, beside its _C module.
     shutil.copyfile(REF / "diff_surfel_rasterization/__init__.py", PKG / "__init__.py")
+    install_twodgs()
     info = {"sources": SOURCES, "ref_root": str(REF), "nvcc_flags": nvcc_flags + common,
             "seconds": round(time.time() - t0, 1),
             "nvcc": subprocess.run(["nvcc", "--version"], capture_output=True, text=True).stdout.strip().splitlines()[-2]}
@@ -117,7 +136,63 @@ def import_reference():
     return mod
 
 
+class _StubMissing:
+    """Meta-path finder that answers imports nothing else can satisfy (plyfile, simple_knn, cv2, matplotlib: the
+    reference imports them at module level, the code paths under test never call them) with MagicMock modules."""
+
+    def find_spec(self, name, path, target=None):
+        import importlib.machinery
+        if name.split(".")[0] not in ("plyfile", "simple_knn", "cv2", "matplotlib", "open3d", "trimesh"):
+            return None
+        return importlib.machinery.ModuleSpec(name, self, is_package=True)
+
+    def create_module(self, spec):
+        from unittest import mock
+        m = mock.MagicMock(name=spec.name)
+        m.__path__, m.__spec__, m.__name__ = [], spec, spec.name
+        return m
+
+    def exec_module(self, module):
+        pass
+
+
+def import_twodgs(op_module, tag: str):
+    """The reference's gaussian_renderer module (unmodified, from oracle/_ref/twodgs) bound to `op_module` as its
+    `diff_surfel_rasterization`.  `tag` names this binding ("b200", "ref"): each gets its own module object, while
+    scene.* / utils.* (operator-independent) are shared.  Returns a namespace: render, GaussianModel, Camera, MiniCam,
+    l1_loss, ssim, module."""
+    import importlib
+    import importlib.util
+    import types
+    if not all((TWODGS_OUT / f).exists() for f in TWODGS_FILES):
+        raise ImportError("oracle/_ref/twodgs is missing: run python oracle/build_ref.py where /root/reference exists")
+    if not any(isinstance(f, _StubMissing) for f in sys.meta_path):
+        sys.meta_path.append(_StubMissing())
+    if str(TWODGS_OUT) not in sys.path:
+        sys.path.insert(0, str(TWODGS_OUT))
+    saved = sys.modules.get("diff_surfel_rasterization")
+    sys.modules["diff_surfel_rasterization"] = op_module
+    try:
+        name = f"_g4s_reference_renderer_{tag}"
+        spec = importlib.util.spec_from_file_location(name, TWODGS_OUT / "gaussian_renderer" / "__init__.py")
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+    finally:
+        if saved is not None:
+            sys.modules["diff_surfel_rasterization"] = saved
+        else:
+            del sys.modules["diff_surfel_rasterization"]
+    gm = importlib.import_module("scene.gaussian_model")
+    cams = importlib.import_module("scene.cameras")
+    lu = importlib.import_module("utils.loss_utils")
+    return types.SimpleNamespace(render=mod.render, GaussianModel=gm.GaussianModel, Camera=cams.Camera, MiniCam=cams.MiniCam,
+                                 l1_loss=lu.l1_loss, ssim=lu.ssim, module=mod)
+
+
 if __name__ == "__main__":
     ok = build(force="--force" in sys.argv)
+    if reference_available():
+        install_twodgs()
     print("oracle/_ref:", "ready" if ok else "unavailable (no /root/reference and no prebuilt files)")
     sys.exit(0 if ok else 1)

@@ -213,7 +213,7 @@ def assert_parity(a: dict, b: dict, keys, rtol=1e-4, max_bad_frac=0.0, max_rel=N
 
 
 # --------------------------------------------------------------------------------- golden files
-OTHER_STAGE_PREFIXES = ("surface_", "mip_filter_", "photometric_", "activations_")
+OTHER_STAGE_PREFIXES = ("surface_", "mip_filter_", "photometric_", "activations_", "regularizers_", "densify_")
 
 
 def rasterizer_golden_files():
