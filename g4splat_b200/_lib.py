@@ -36,6 +36,8 @@ SIGNATURES = {
     "g4s_densify_stats_multimem": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4s_photometric_forward": (_i, [_i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp]),
     "g4s_photometric_backward": (_i, [_i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp]),
+    "g4s_densify_classify": (_i, [_i, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _vp, _vp]),
+    "g4s_densify_gather": (_i, [_i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "g4s_multimem_allreduce": (_i, [_vp, _i64, _vp, _i64, _i, _i, _vp]),
     "g4s_normal2curv_forward": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp]),
     "g4s_normal2curv_backward": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp]),

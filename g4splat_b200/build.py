@@ -13,7 +13,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 ROOT = PKG.parent
 LIB = PKG / "libg4s_rasterizer.so"
-SOURCES = ["api.cu", "project.cu", "binning.cu", "blend.cu", "surface.cu", "gaussian_model.cu", "loss.cu", "regularizers.cu"]
+SOURCES = ["api.cu", "project.cu", "binning.cu", "blend.cu", "surface.cu", "gaussian_model.cu", "loss.cu", "regularizers.cu", "densify.cu"]
 HEADERS = ["common.cuh", "kernels.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--cudart", "shared"]

@@ -384,6 +384,29 @@ int g4s_densify_stats_multimem(int P, const float* dL_dmeans2D, const int* radii
     return densify_stats_impl(P, dL_dmeans2D, radii, accum_mc, denom_mc, max_radii_mc, 1, stream);
 }
 
+int g4s_densify_classify(int P, const float* accum, const float* denom, const float* scaling_raw, const float* opacity_raw,
+                         float grad_threshold, float dense_extent, float min_opacity, float big_world_size, int n_split,
+                         uint8_t* flags, void* stream) {
+    if (P < 0 || n_split < 1) return fail(G4S_EINVAL, "g4s_densify_classify: bad P / n_split");
+    if (P == 0) return G4S_OK;
+    if (!accum || !denom || !scaling_raw || !opacity_raw || !flags) return fail(G4S_EINVAL, "g4s_densify_classify: null buffer");
+    launch_densify_classify(P, accum, denom, scaling_raw, opacity_raw, grad_threshold, dense_extent, min_opacity, big_world_size,
+                            1.0f / (0.8f * (float)n_split), flags, (cudaStream_t)stream);
+    return stage_check(false, (cudaStream_t)stream, "densify_classify");
+}
+int g4s_densify_gather(int P_new, int rest_width, const int* src_row, const uint8_t* kind, const int* sample_row,
+                       const float* samples, int n_split, const float* const* src_tensors, float* const* dst_tensors, void* stream) {
+    if (P_new < 0 || rest_width < 0 || n_split < 1) return fail(G4S_EINVAL, "g4s_densify_gather: bad sizes");
+    if (P_new == 0) return G4S_OK;
+    if (!src_row || !kind || !sample_row || !src_tensors || !dst_tensors) return fail(G4S_EINVAL, "g4s_densify_gather: null buffer");
+    for (int i = 0; i < 18; i += 3)
+        if ((!src_tensors[i] || !dst_tensors[i]) && !(i == 6 && rest_width == 0))
+            return fail(G4S_EINVAL, "g4s_densify_gather: null parameter tensor");
+    launch_densify_gather(P_new, rest_width, src_row, kind, sample_row, samples, 1.0f / (0.8f * (float)n_split), src_tensors, dst_tensors,
+                          (cudaStream_t)stream);
+    return stage_check(false, (cudaStream_t)stream, "densify_gather");
+}
+
 int g4s_multimem_allreduce(float* sum_mc, int64_t n_floats, int* max_mc, int64_t n_ints, int rank, int world, void* stream) {
     if (n_floats < 0 || n_ints < 0 || world < 1 || rank < 0 || rank >= world || (n_floats & 3))
         return fail(G4S_EINVAL, "g4s_multimem_allreduce: bad sizes (n_floats must be a multiple of 4)");

@@ -85,7 +85,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(TileScanArgs a)
     }
     if (tid == SCAN_THREADS - 1) {
         a.tile_offset[T] = run;
-        a.counters[CNT_RENDERED] = (int32_t)run;
+        // The instance count is scanned in 32 bits.  A total above INT32_MAX cannot be represented in the counter the
+        // guards of every later kernel compare with `capacity`: saturate it (the guards then always refuse, the host
+        // sees a count no capacity can satisfy and fails the call) instead of wrapping negative and passing them.
+        a.counters[CNT_RENDERED] = run > 0x7fffffffu ? 0x7fffffff : (int32_t)run;
     }
     if (tid == 0) a.counters[CNT_MAXLEN] = (int32_t)s_max;
 }

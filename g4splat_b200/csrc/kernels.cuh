@@ -121,6 +121,13 @@ void launch_photometric_fwd(int W, int H, int C, const float* img, const float* 
 void launch_photometric_bwd(int W, int H, int C, const float* img, const float* gt, const float* window11, float lambda,
                             const float* dmaps, const float* dL_dloss, float* dL_dimg, cudaStream_t s);
 
+// ---- densification (densify.cu) ------------------------------------------------------------------
+void launch_densify_classify(int P, const float* accum, const float* denom, const float* scaling, const float* opacity,
+                             float grad_threshold, float dense_extent, float min_opacity, float big_ws, float child_scale,
+                             uint8_t* flags, cudaStream_t s);
+void launch_densify_gather(int P_new, int rest_w, const int* src_row, const uint8_t* kind, const int* sample_row, const float* samples,
+                           float child_scale, const float* const* src, float* const* dst, cudaStream_t s);
+
 // ---- image-space regularisers (regularizers.cu) -------------------------------------------------
 void launch_normal2curv_fwd(int W, int H, const float* normal, const float* mask, float* curv, float* sg, cudaStream_t s);
 void launch_normal2curv_bwd(int W, int H, const float* mask, const float* sg, const float* g_curv, float* g_normal, cudaStream_t s);

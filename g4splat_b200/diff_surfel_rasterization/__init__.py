@@ -323,6 +323,9 @@ def _plan_and_render(dev, P, W, H, bg, rs, plan):
             _capacity.observe(dev_index, num_rendered)
             if num_rendered <= cap:
                 break
+            if num_rendered >= 0x7fffffff:
+                raise RuntimeError("g4s rasterizer: more than 2^31 - 1 (Gaussian, tile) instances in one view "
+                                   "(the reference fails to allocate its sort buffers at this size)")
             cap = _capacity.bucket(num_rendered + 65536)  # the speculative launch was a no-op: re-issue
         if debug and rs.prefiltered and int(counts[3]) != 0:
             raise RuntimeError("Point is filtered although prefiltered is set. This shouldn't happen!")

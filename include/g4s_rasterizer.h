@@ -192,6 +192,26 @@ int g4s_densify_stats(int P, const float* dL_dmeans2D, const int* radii, float* 
 int g4s_densify_stats_multimem(int P, const float* dL_dmeans2D, const int* radii, float* accum_mc, float* denom_mc,
                                int* max_radii_mc, void* stream);
 
+/* ---- adaptive density control --------------------------------------------------------------------
+ * Replaces GaussianModel.densify_and_prune and its helpers (2DGS/scene/gaussian_model.py:528-647; driven from
+ * train_with_refine_depth.py:582-599): ~60 torch kernels (masks, masked gathers, cats, for six parameters and both
+ * Adam moments, three times) become two.
+ * g4s_densify_classify: per Gaussian, from accum / denom (xyz_gradient_accum, denom), the raw scaling [P,2] and raw
+ *   opacity [P]: flags[i] bit 0 = cloned (|grad| >= grad_threshold, max scale <= dense_extent = percent_dense * extent),
+ *   bit 1 = split (same gradient test, max scale > dense_extent), bit 2 = the Gaussian (and its clone) is pruned at the
+ *   end (sigmoid(opacity) < min_opacity, or max scale > big_world_size when big_world_size >= 0), bit 3 = its split
+ *   children (scale / (0.8 n_split)) are pruned.
+ * g4s_densify_gather: writes the P_new final rows.  src_row[j] = source Gaussian of output row j, kind[j] = 0 survivor /
+ *   1 clone / 2 split child, sample_row[j] = row of `samples` ([n,3], the caller's torch.normal draw) for children.
+ *   src_tensors / dst_tensors: HOST arrays of 18 device pointers = {xyz, features_dc, features_rest, opacity, scaling,
+ *   rotation} x {parameter, exp_avg, exp_avg_sq}; moment pointers may be NULL (no optimizer state).  Children get
+ *   xyz + R(q) sample and log(exp(scaling) / (0.8 n_split)); new rows get zero moments. */
+int g4s_densify_classify(int P, const float* accum, const float* denom, const float* scaling_raw, const float* opacity_raw,
+                         float grad_threshold, float dense_extent, float min_opacity, float big_world_size, int n_split,
+                         uint8_t* flags, void* stream);
+int g4s_densify_gather(int P_new, int rest_width, const int* src_row, const uint8_t* kind, const int* sample_row,
+                       const float* samples, int n_split, const float* const* src_tensors, float* const* dst_tensors, void* stream);
+
 /* ---- gradient all-reduce of the view-sharded trainer over NVSwitch multicast ---------------------
  * sum_mc / max_mc: MULTICAST addresses (CUDA multicast object; torch symmetric memory's multicast_ptr) of an fp32
  * block of n_floats (multiple of 4, 16-byte aligned) and an int32 block of n_ints that every rank holds at the same

@@ -9,7 +9,8 @@ once with `diff_surfel_rasterization` bound to the B200 operator, once bound to 
   (i)  one render(): every entry of the result dict and every leaf gradient
        (gaussian_renderer/__init__.py:19-166);
   (ii) 100 Adam iterations shaped like train_with_refine_depth.py:378-399,496,602-604 (L1 + D-SSIM + normal
-       consistency + distortion, GaussianModel.training_setup's optimizer, update_learning_rate): the two loss curves.
+       consistency + distortion, GaussianModel.training_setup's optimizer, update_learning_rate): the two loss curves,
+       judged against the drift between two runs of the reference itself (its atomics are not deterministic).
 
 The reference extension is the checker here (test infrastructure); the product path never sees it."""
 import math
@@ -123,7 +124,10 @@ def test_training_curves_of_both_operators_agree():
             gts.append(ref.render(_camera(ref, c, device), gm0, pipe, bg)["render"].clamp(0, 1))
         del gm0
     curves = {}
-    for name, ns in (("b200", b200), ("ref", ref)):
+    # the reference runs twice: its backward accumulates with fp32 atomics in scheduling order, and Adam (eps = 1e-15)
+    # turns that last-bit noise into O(lr) parameter differences wherever a gradient is near zero, so two runs of the
+    # SAME reference code drift apart.  That drift is the yardstick for the operator swap.
+    for name, ns in (("b200", b200), ("ref", ref), ("ref_again", ref)):
         gm = _model(ns, P, cfg["seed"], device)
         gm.training_setup(opt)
         views = [_camera(ns, c, device) for c in cams]
@@ -147,9 +151,14 @@ def test_training_curves_of_both_operators_agree():
             losses.append(float(total))
         curves[name] = np.array(losses)
         del gm
-    a, b = curves["b200"], curves["ref"]
+    a, b, b2 = curves["b200"], curves["ref"], curves["ref_again"]
     assert b[-10:].mean() < b[:10].mean(), "the reference run itself did not train"
-    rel = np.abs(a - b) / np.abs(b)
-    # identical forward bits, gradients equal to ~1e-6: the curves stay together to fp32 noise amplified by Adam
-    assert rel.max() <= 1e-3, (float(rel.max()), int(rel.argmax()))
+    swap = np.abs(a - b) / np.abs(b)            # operator swapped
+    noise = np.abs(b2 - b) / np.abs(b)          # nothing swapped: the reference against itself
+    print("relative loss difference, max over 100 iterations: operator swap %.3e, reference vs itself %.3e" % (swap.max(), noise.max()))
+    # before the drift builds up the curves are the same to fp32 rounding (identical forward bits, gradients equal to ~1e-6)
+    assert swap[:5].max() <= 1e-5, swap[:5]
+    # afterwards the swap must be indistinguishable from the reference's own run-to-run drift
+    assert swap.max() <= max(1e-3, 3.0 * noise.max()), (float(swap.max()), float(noise.max()))
+    assert abs(a[-10:].mean() - b[-10:].mean()) <= max(1e-3, 3.0 * noise.max()) * abs(b[-10:].mean())
     assert math.isfinite(a[-1])

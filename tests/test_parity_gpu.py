@@ -480,3 +480,159 @@ def test_nonfinite_upstream_grads_at_empty_pixels_are_ignored(b200):
     for k in Hh.GRAD_KEYS:
         assert np.isfinite(got[k]).all(), k
     Hh.assert_parity(got, base, Hh.GRAD_KEYS, rtol=1e-5, max_bad_frac=GRAD_BUDGET, what="poisoned upstream")
+
+
+# ------------------------------------------------------------------------------- round 2 additions
+FAST_FLIP_BUDGET = 2e-5   # fraction of image elements a fast-math forward may move by more than 1e-4 (threshold flips)
+
+
+@pytest.mark.parametrize("cfg", ["c0", "c1", "c2"])
+def test_fast_math_forward_stays_within_north_star_tolerance(cfg, b200, reference):
+    """The opt-in fast forward (rcp.approx / ex2.approx, set_fast_math) against the reference extension: 1e-4 relative
+    with a COUNTED flip budget (a pixel whose alpha, T < 1e-4 or T > 0.5 decision sits within an ulp of its threshold),
+    gradients within 1e-4; radii (projection stage, untouched) identical.  The exact mode is what every other test runs."""
+    from g4splat_b200 import synthetic as S
+    c = S.CONFIGS[cfg]
+    case = Hh.room_case(cfg, P=c["P"], W=c["W"], H=c["H"], seed=c["seed"], cams=c["cams"])
+    want = Hh.run_operator(reference, case)
+    prev = b200.set_fast_math(True)
+    try:
+        got = Hh.run_operator(b200, case)
+    finally:
+        b200.set_fast_math(prev)
+    assert Hh.radii_mismatch(got["radii"], want["radii"]) == 0
+    Hh.assert_parity(got, want, ("color", "allmap"), rtol=1e-4, max_bad_frac=FAST_FLIP_BUDGET, what=f"{cfg} fast forward vs reference")
+    Hh.assert_parity(got, want, Hh.GRAD_KEYS, rtol=1e-4, max_bad_frac=GRAD_BUDGET, what=f"{cfg} backward after fast forward vs reference")
+    assert not np.array_equal(got["color"], want["color"]) or cfg == "c0"   # it really is a different arithmetic
+    assert b200._LIB.g4s_get_fast_math() == int(prev)
+
+
+def test_gradient_sink_with_P_not_a_multiple_of_four(b200):
+    """the 16-byte SH reductions of the sink path need aligned rows; the flat buffer pads its blocks and the
+    kernel falls back to scalar reductions for a misaligned destination.  P = 20_003, three views, both layouts."""
+    import torch
+    from g4splat_b200 import synthetic as S
+    from g4splat_b200.view_parallel import ViewShardedGradSync
+    P, W, H = 20_003, 320, 200
+    sc = S.make_scene(P, 5)
+    dev = "cuda"
+    t = lambda a: torch.from_numpy(a).to(dev).requires_grad_(True)
+    params = {"xyz": t(sc["means3D"]), "features": t(sc["shs"]), "opacity": t(sc["opacities"]), "scaling": t(sc["scales"]),
+              "rotation": t(sc["rotations"])}
+    cams = S.make_cameras(3, W, H)
+    singles = [Hh.run_operator(b200, Hh.Case("v", sc, cam, grad_seed=3)) for cam in cams]
+
+    def run(sink_features):
+        for p in params.values():
+            p.grad = None
+        b200.set_gradient_sink({params["features"]: sink_features} if sink_features is not None else None)
+        for cam in cams:
+            c2 = Hh.Case("v", sc, cam, grad_seed=3)
+            rast = b200.GaussianRasterizer(Hh.make_settings(b200, c2, dev))
+            m2d = torch.zeros_like(params["xyz"], requires_grad=True)
+            color, radii, allmap = rast(means3D=params["xyz"], means2D=m2d, opacities=params["opacity"], shs=params["features"],
+                                        scales=params["scaling"], rotations=params["rotation"])
+            gc, go = c2.upstream()
+            torch.autograd.backward([color, allmap], [torch.from_numpy(gc).to(dev), torch.from_numpy(go).to(dev)])
+        b200.set_gradient_sink(None)
+
+    want = sum(s["dL_dsh"] for s in singles)
+    # (a) a deliberately MISALIGNED sink buffer (4 bytes past a 16-byte boundary): scalar reductions
+    backing = torch.zeros(P * 48 + 1, device=dev)
+    mis = backing[1:].view(P, 16, 3)
+    assert mis.data_ptr() % 16 == 4
+    run(mis)
+    assert Hh.parity(mis.cpu().numpy(), want, 1e-4)["bad_frac"] == 0
+    # (b) the padded flat buffer of the view-sharded trainer: every block starts on a 128-byte boundary whatever P is
+    sync = ViewShardedGradSync(params)
+    assert all(v.data_ptr() % 128 == 0 for v in sync._views.values())
+    sync.bind(b200)
+    for cam in cams:
+        c2 = Hh.Case("v", sc, cam, grad_seed=3)
+        rast = b200.GaussianRasterizer(Hh.make_settings(b200, c2, dev))
+        m2d = torch.zeros_like(params["xyz"], requires_grad=True)
+        color, radii, allmap = rast(means3D=params["xyz"], means2D=m2d, opacities=params["opacity"], shs=params["features"],
+                                    scales=params["scaling"], rotations=params["rotation"])
+        gc, go = c2.upstream()
+        torch.autograd.backward([color, allmap], [torch.from_numpy(gc).to(dev), torch.from_numpy(go).to(dev)])
+    b200.set_gradient_sink(None)
+    for name, key in (("xyz", "dL_dmeans3D"), ("features", "dL_dsh"), ("opacity", "dL_dopacity"), ("scaling", "dL_dscales"),
+                      ("rotation", "dL_drotations")):
+        assert Hh.parity(params[name].grad.cpu().numpy(), sum(s[key] for s in singles), 1e-4)["bad_frac"] == 0, name
+
+
+def test_gradient_sink_entry_dies_with_its_parameter(b200):
+    """a sink entry must not outlive its parameter (a new tensor reusing the address would otherwise have its
+    gradient silently added to a stale buffer)."""
+    import gc
+    import torch
+    p = torch.zeros(8, 3, device="cuda", requires_grad=True)
+    buf = torch.zeros(8, 3, device="cuda")
+    b200.set_gradient_sink({p: buf})
+    assert b200._sink_for(p) is not None
+    q = torch.zeros(8, 3, device="cuda", requires_grad=True)      # same shape, different tensor
+    assert b200._sink_for(q) is None
+    del p
+    gc.collect()
+    r = torch.zeros(8, 3, device="cuda", requires_grad=True)      # may reuse the freed address and even the id
+    assert b200._sink_for(r) is None
+    b200.set_gradient_sink(None)
+
+
+def test_raw_parameter_operator_accumulates_into_the_gradient_sink(b200, oracle32):
+    """The multi-view gradient sink through rasterize_gaussian_model (the trainer's un-activated leaves): two views
+    accumulated by the kernel == the sum of two single-view autograd gradients."""
+    import torch
+    from g4splat_b200 import synthetic as S
+    case = Hh.named_case("ragged", oracle32)
+    sc, dev = case.scene, "cuda"
+    op = np.clip(sc["opacities"], 1e-4, 1 - 1e-4)
+    leaf = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev).requires_grad_(True)
+    leaves = dict(xyz=leaf(sc["means3D"]), dc=leaf(sc["shs"][:, :1]), rest=leaf(sc["shs"][:, 1:]), opacity=leaf(np.log(op / (1 - op))),
+                  scaling=leaf(np.log(sc["scales"])), rotation=leaf(sc["rotations"]))
+    cams = S.make_cameras(2, case.cam.W, case.cam.H)
+
+    def render(cam):
+        c2 = Hh.Case("v", sc, cam, sh_degree=case.sh_degree, grad_seed=3)
+        m2d = torch.zeros_like(leaves["xyz"], requires_grad=True)
+        color, radii, allmap = b200.rasterize_gaussian_model(leaves["xyz"], m2d, leaves["dc"], leaves["rest"], leaves["opacity"],
+                                                             leaves["scaling"], leaves["rotation"], None, Hh.make_settings(b200, c2, dev))
+        gc, go = c2.upstream()
+        torch.autograd.backward([color, allmap], [torch.from_numpy(gc).to(dev), torch.from_numpy(go).to(dev)])
+
+    for cam in cams:
+        render(cam)
+    want = {k: v.grad.clone() for k, v in leaves.items()}
+    for v in leaves.values():
+        v.grad = None
+    sinks = {k: torch.zeros_like(v) for k, v in leaves.items()}
+    b200.set_gradient_sink({leaves[k]: sinks[k] for k in leaves})
+    for cam in cams:
+        render(cam)
+    b200.set_gradient_sink(None)
+    for k, v in leaves.items():
+        assert v.grad is None, k                                   # nothing went through autograd
+        assert Hh.parity(sinks[k].cpu().numpy(), want[k].cpu().numpy(), 1e-4)["bad_frac"] == 0, k
+
+
+def test_unsynchronised_forward_overflow_is_reported_before_its_backward(b200, oracle32, monkeypatch):
+    """G4S_SYNC=none with a capacity that is too small -- the forward kernels are no-ops, the backward kernels
+    refuse to walk the unwritten lists, and the host raises when the backward is requested (not one call later)."""
+    import torch
+    case = Hh.named_case("c0", oracle32)
+    monkeypatch.setenv("G4S_SYNC", "none")
+    dev_index = torch.cuda.current_device()
+    saved = dict(b200._capacity.cap)
+    b200._capacity.cap[dev_index] = 1 << 10          # far below the ~60 k instances of this view
+    try:
+        with pytest.raises(RuntimeError, match="capacity"):
+            Hh.run_operator(b200, case)
+    finally:
+        b200._capacity.cap.clear()
+        b200._capacity.cap.update(saved)
+        b200._state(torch.device("cuda", dev_index)).pending_overflow.clear()
+    monkeypatch.delenv("G4S_SYNC")
+    torch.cuda.synchronize()
+    got = Hh.run_operator(b200, case)                  # the device is healthy and the next call is correct
+    want = Hh.run_oracle(oracle32, case)
+    Hh.assert_parity(got, want, ("color", "allmap"), rtol=1e-4, max_bad_frac=FWD_BUDGET, what="after an overflowed call")
