@@ -192,6 +192,31 @@ def path_bytes(P, V, R, N, K, M):
 
 
 # ------------------------------------------------------------------------------------- workload
+def cached_scene(cfg_name: str, P: int, seed: int, rank: int, world: int):
+    """The seeded synthetic scene.  Generating 5 M surfels takes ~20 s of numpy per process; on a multi-rank run
+    local rank 0 generates it once into /dev/shm and the others read it (same bytes: the generator is seeded)."""
+    from g4splat_b200 import synthetic as S
+    if P < 2_000_000:
+        return S.make_scene(P, seed)
+    path = Path("/dev/shm") / f"g4s_scene_{cfg_name}_{P}_{seed}.npz"
+    keys = ("means3D", "scales", "rotations", "opacities", "shs")
+    if not path.exists() and rank == 0:
+        sc = S.make_scene(P, seed)
+        tmp = path.with_suffix(".tmp.npz")
+        np.savez(tmp, **sc)
+        os.replace(tmp, path)
+        return sc
+    if world > 1 or path.exists():
+        deadline = time.time() + 600
+        while not path.exists():
+            if time.time() > deadline:
+                return S.make_scene(P, seed)
+            time.sleep(0.5)
+        z = np.load(path)
+        return {k: z[k] for k in keys}
+    return S.make_scene(P, seed)
+
+
 class Workload:
     def __init__(self, device, views_per_step: int, rank: int, world: int, cfg_name: str = CONFIG):
         import torch
@@ -199,7 +224,7 @@ class Workload:
         cfg = S.CONFIGS[cfg_name]
         self.cfg, self.device, self.vps, self.rank, self.world = cfg, device, views_per_step, rank, world
         self.P, self.W, self.H = cfg["P"], cfg["W"], cfg["H"]
-        sc = S.make_scene(self.P, cfg["seed"])
+        sc = cached_scene(cfg_name, self.P, cfg["seed"], rank, world)
         t = lambda a: torch.from_numpy(a).to(device).requires_grad_(True)
         # 58 floats per Gaussian (xyz 3, SH 48, opacity 1, scaling 2, rotation 4), already activated:
         # the operator's inputs.  (The trainer's activations / cat of features_dc and features_rest sit

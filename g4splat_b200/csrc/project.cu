@@ -845,19 +845,32 @@ __global__ void __launch_bounds__(256) densify_stats_kernel(int P, const float* 
 // crosses each link once per direction (a ring all-reduce moves 2 (N-1)/N of the buffer in N-1 dependent hops).
 // The int32 block behind the floats (max_radii2D) is combined with max instead of add.  The caller brackets the
 // kernel with barriers (all partial sums complete before, all slices written after).
-__global__ void __launch_bounds__(512) multimem_allreduce_kernel(float* mc, size_t n_add_quads, size_t q_begin, size_t q_end,
-                                                                int* mc_max, size_t m_begin, size_t m_end) {
+__global__ void __launch_bounds__(512) multimem_allreduce_kernel(float* mc, size_t q_begin, size_t q_end, int* mc_max, size_t m_begin,
+                                                                size_t m_end) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t q = q_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < q_end; q += stride) {
-        float4 v;
-        float* p = mc + 4 * q;
-        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
-                     ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    const size_t first = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // four independent 16-byte reductions in flight per thread: the round trip through the switch is long
+    constexpr int U = 4;
+    size_t q = q_begin + first;
+    for (; q + (U - 1) * stride < q_end; q += U * stride) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "l"(mc + 4 * (q + u * stride)) : "memory");
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                         ::"l"(mc + 4 * (q + u * stride)), "f"(v[u].x), "f"(v[u].y), "f"(v[u].z), "f"(v[u].w) : "memory");
     }
-    (void)n_add_quads;
-    for (size_t i = m_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m_end; i += stride) {
+    for (; q < q_end; q += stride) {
+        float4 v;
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc + 4 * q) : "memory");
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                     ::"l"(mc + 4 * q), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    }
+    for (size_t i = m_begin + first; i < m_end; i += stride) {
         int v;
         int* p = mc_max + i;
         asm volatile("multimem.ld_reduce.relaxed.sys.global.max.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -869,7 +882,7 @@ void launch_multimem_allreduce(float* mc, size_t n_floats, int* mc_max, size_t n
     const size_t qb = quads * rank / world, qe = quads * (rank + 1) / world;
     const size_t mb = n_ints * rank / world, me = n_ints * (rank + 1) / world;
     if (qe == qb && me == mb) return;
-    multimem_allreduce_kernel<<<148 * 4, 512, 0, s>>>(mc, quads, qb, qe, mc_max, mb, me);
+    multimem_allreduce_kernel<<<148 * 4, 512, 0, s>>>(mc, qb, qe, mc_max, mb, me);
     count_launch();
 }
 

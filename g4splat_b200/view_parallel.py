@@ -92,14 +92,27 @@ class ViewShardedGradSync:
         self._symm = None
         self._bound_module = None
         self._bound_names = None
+        requested = transport
         if transport == "auto":
             transport = os.environ.get("G4S_TRANSPORT", "auto")
+            requested = transport
         if transport == "auto":
             transport = "multimem" if (use_native and multimem_available(group)) else "nccl"
         if transport not in ("nccl", "multimem", "multimem_red"):
             raise ValueError(f"unknown transport {transport!r}")
         self.transport = transport
-        self._build(params)
+        try:
+            self._build(params)
+        except Exception as ex:  # noqa: BLE001
+            if requested != "auto" or transport == "nccl":
+                raise
+            # "auto" promised a working transport: the multicast mapping was refused (no NVLS fabric in this container,
+            # a driver without multicast objects, ...).  Every rank takes the same decision.
+            import warnings
+            warnings.warn(f"view_parallel: multicast transport unavailable ({ex}); falling back to NCCL")
+            self.transport = "nccl"
+            self._symm = None
+            self._build(params)
 
     # -- layout ---------------------------------------------------------------------------------
     def _build(self, params: Dict[str, torch.Tensor]) -> None:

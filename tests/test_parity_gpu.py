@@ -636,3 +636,23 @@ def test_unsynchronised_forward_overflow_is_reported_before_its_backward(b200, o
     got = Hh.run_operator(b200, case)                  # the device is healthy and the next call is correct
     want = Hh.run_oracle(oracle32, case)
     Hh.assert_parity(got, want, ("color", "allmap"), rtol=1e-4, max_bad_frac=FWD_BUDGET, what="after an overflowed call")
+
+
+def test_backward_kernel_variant_pair_matches_reference(tmp_path):
+    """G4S_BWD=pair (the 8x4-region backward that DESIGN.md 4 measures the default against) is selected once per process:
+    run two small side-by-side cases in a subprocess with the variable set."""
+    import subprocess
+    code = (
+        "import sys; sys.path.insert(0, 'tests'); import numpy as np; import helpers as Hh\n"
+        "import g4splat_b200.diff_surfel_rasterization as b200\n"
+        "from oracle import build_ref; from oracle.oracle import Oracle\n"
+        "ref = build_ref.import_reference(); o = Oracle('f32')\n"
+        "for name in ('ragged', 'c0_bg'):\n"
+        "    case = Hh.named_case(name, o)\n"
+        "    want = Hh.run_operator(ref, case); got = Hh.run_operator(b200, case)\n"
+        "    Hh.assert_parity(got, want, Hh.GRAD_KEYS, rtol=1e-4, max_bad_frac=2e-4, what=name)\n"
+        "    assert np.array_equal(got['color'], want['color'])\n"
+        "print('pair ok')\n")
+    env = dict(os.environ, G4S_BWD="pair")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, env=env, timeout=600)
+    assert res.returncode == 0 and "pair ok" in res.stdout, res.stdout[-2000:] + res.stderr[-3000:]
