@@ -28,6 +28,7 @@ when that build is absent it falls back to timing the CPU oracle port.
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -278,12 +279,11 @@ class Workload:
         """Cameras this rank renders in step `step` (rank / world default to the process's own)."""
         rank = self.rank if rank is None else rank
         world = self.world if world is None else world
-        if self.doc["step_views"] is not None:      # strong scaling: the step's views are sharded over the ranks
-            from g4splat_b200.view_parallel import shard_views
-            n = self.doc["step_views"]
-            return [(step * n + i) % self.ring for i in shard_views(n, world, rank)]
-        base = (step * world + rank) * self.vps
-        return [(base + i) % self.ring for i in range(self.vps)]
+        # the step's views are dealt out to the ranks (shard_views(strided=True)): neighbouring ring cameras cost
+        # about the same, a contiguous block per rank would make the step wait for the rank with the expensive arc
+        from g4splat_b200.view_parallel import shard_views
+        n = self.doc["step_views"] if self.doc["step_views"] is not None else self.vps * world
+        return [(step * n + i) % self.ring for i in shard_views(n, world, rank, strided=True)]
 
     def views_per_step_total(self):
         return self.doc["step_views"] if self.doc["step_views"] is not None else self.vps * self.world
@@ -306,6 +306,10 @@ class Workload:
         return color, radii, allmap, means2D
 
 
+# G4S_BENCH_PIPELINE=1: view_batch() around the views of a step (B200 arm).  Off by default: measured on a B200 it
+# gains 3 % in one loop and loses in another (the blend kernels already fill ~70 % of the issue slots, the side
+# stream's kernels take what they gain), so the headline runs the plain single-stream loop.
+PIPELINE = os.environ.get("G4S_BENCH_PIPELINE", "0") == "1"
 STEP_TRACE = []   # G4S_BENCH_TRACE=1: a CUDA event after every step (diagnostics; read after the timed region)
 
 
@@ -321,23 +325,26 @@ def run_steps(wl: Workload, mod, sync, steps: int, first_step: int, e2e: bool):
             ev.record()
             STEP_TRACE.append((s, e2e, ev, op_counts_snapshot(mod)))
         loss_acc = None
-        for k, vid in enumerate(wl.view_ids(s)):
-            if e2e:
-                nxt = wl.prefetch_image(s + k + 1)           # next view's photograph: PCIe copy overlaps this view
-            color, radii, allmap, means2D = wl.rasterize(mod, vid)
-            if e2e:
-                gt = torch.mul(wl.image(slot), 1.0 / 255.0)      # uint8 -> float32 in one kernel
-                wl.release_image(slot)
-                slot = nxt
-                # L1 photometric term + regularisers on the seven allmap channels:
-                #   mean|color - gt| + 0.05 mean(distortion) + 0.01 mean(depth + median depth) + 0.01 mean(alpha, normal)
-                # written as one weighted sum so that both arms spend few launches on it
-                loss = torch.nn.functional.l1_loss(color, gt) + (allmap * wl.reg_weights).sum()
-                loss.backward()
-                loss_acc = loss.detach() if loss_acc is None else loss_acc + loss.detach()
-            else:
-                torch.autograd.backward([color, allmap], [wl.g_color, wl.g_allmap])
-            sync.add_view_stats(means2D.grad, radii)
+        # the views of a step share one parameter set: the B200 operator may run each view's front end ahead of the
+        # previous view's blend kernels (view_batch); the reference operator has no such mode
+        with (mod.view_batch() if PIPELINE and hasattr(mod, "view_batch") else contextlib.nullcontext()):
+            for k, vid in enumerate(wl.view_ids(s)):
+                if e2e:
+                    nxt = wl.prefetch_image(s + k + 1)           # next view's photograph: PCIe copy overlaps this view
+                color, radii, allmap, means2D = wl.rasterize(mod, vid)
+                if e2e:
+                    gt = torch.mul(wl.image(slot), 1.0 / 255.0)      # uint8 -> float32 in one kernel
+                    wl.release_image(slot)
+                    slot = nxt
+                    # L1 photometric term + regularisers on the seven allmap channels:
+                    #   mean|color - gt| + 0.05 mean(distortion) + 0.01 mean(depth + median depth) + 0.01 mean(alpha, normal)
+                    # written as one weighted sum so that both arms spend few launches on it
+                    loss = torch.nn.functional.l1_loss(color, gt) + (allmap * wl.reg_weights).sum()
+                    loss.backward()
+                    loss_acc = loss.detach() if loss_acc is None else loss_acc + loss.detach()
+                else:
+                    torch.autograd.backward([color, allmap], [wl.g_color, wl.g_allmap])
+                sync.add_view_stats(means2D.grad, radii)
         sync.allreduce()
         if e2e:
             last = float(loss_acc.item())  # device -> host read of the step's result
@@ -545,6 +552,7 @@ def main():
                     help="N > 1: how the ranks' gradient sums meet (g4splat_b200/view_parallel.py)")
     ap.add_argument("--math", default="exact", choices=["exact", "fast"],
                     help="forward blend arithmetic: exact = bit-identical to the reference (default), fast = rcp/ex2.approx")
+    ap.add_argument("--no-fast-math", action="store_true", help="skip the informational fast-math timing")
     ap.add_argument("--no-check", action="store_true", help="N > 1: skip the N-rank == 1-rank gradient self-check")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-iteration", action="store_true", help="skip the informational whole-iteration timing")
@@ -652,6 +660,18 @@ def main():
     h2d = len(wl.view_ids(0)) * (3 * N)   # one uint8 image per view of this rank
     d2h = 4                             # the scalar loss
 
+    # ---- the opt-in fast forward, same loop (informational; the headline `value` above is the exact mode) ---------
+    fast = None
+    if lib is not None and args.math == "exact" and not args.no_fast_math:
+        mod.set_fast_math(True)
+        run_steps(wl, mod, sync, 2, 2000, e2e=False)
+        k_fast = max(3, args.steps // 2)
+        ms_fast, _ = time_region(lambda: run_steps(wl, mod, sync, k_fast, 2002, e2e=False), device, dist_on)
+        mod.set_fast_math(False)
+        fast = {"value": P * views_total * k_fast / (ms_fast * 1e-3), "unit": UNIT, "ms_per_step": ms_fast / k_fast, "steps": k_fast,
+                "what": "set_fast_math(True): rcp.approx / ex2.approx in the forward blend; 1e-4 parity with <= 2e-5 of the image "
+                        "elements flipping a threshold (tests/test_parity_gpu.py::test_fast_math_forward_stays_within_north_star_tolerance)"}
+
     train_it = None
     if world == 1 and not args.no_train_iteration:
         sync.zero()
@@ -701,6 +721,7 @@ def main():
                        "l2_policy": f"inputs larger than L2: {232 * P // 1_000_000} MB of parameters + {192 * P // 1_000_000} MB of SH gradients per view, a different camera every view",
                        "untimed_steps_before_timing": settle + 1,
                        "math": args.math if args.impl != "reference" else "reference",
+                       "view_pipeline": bool(PIPELINE and args.impl != "reference"),
                        "transport": sync.transport if world > 1 else None,
                        "parallelism": f"view-sharded dp{world}"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -708,6 +729,8 @@ def main():
             "gpu_launches": launches, "clocks": clk}
     if train_it is not None:
         line["train_iteration"] = train_it
+    if fast is not None:
+        line["fast_math"] = fast
     if check is not None:
         line["allreduce_check"] = check
     if world > 1:

@@ -24,6 +24,8 @@ SIGNATURES = {
     "g4s_forward_plan": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp,
                               _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _i]),
     "g4s_forward_render": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i]),
+    "g4s_forward_bin": (_i, [_i, _i, _i, _vp, _vp, _vp, _i64, _vp, _i]),
+    "g4s_forward_blend": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i]),
     "g4s_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _f, _f,
                           _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i]),
     "g4s_backward_scratch_bytes_raw": (_sz, [_i]),

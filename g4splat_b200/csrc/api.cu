@@ -211,13 +211,12 @@ int g4s_forward_plan_raw(int P, int D, int M, int W, int H, const float* xyz, co
                              host_counts, stream, debug, 1, features_rest, mip_filter);
 }
 
-int g4s_forward_render(int P, int W, int H, const float* background, const void* geom_buffer,
-                       void* img_buffer, void* binning_buffer, int64_t capacity, float* out_color,
-                       float* out_others, void* stream, int debug) {
+// stage 1 of the render call: scatter + per-tile sort (everything between the plan and the blend)
+int g4s_forward_bin(int P, int W, int H, const void* geom_buffer, void* img_buffer, void* binning_buffer, int64_t capacity,
+                    void* stream, int debug) {
     cudaStream_t s = (cudaStream_t)stream;
-    if (P < 0 || W <= 0 || H <= 0 || capacity < 0) return fail(G4S_EINVAL, "g4s_forward_render: bad sizes");
-    if (!geom_buffer || !img_buffer || !binning_buffer || !out_color || !out_others || !background)
-        return fail(G4S_EINVAL, "g4s_forward_render: null buffer");
+    if (P < 0 || W <= 0 || H <= 0 || capacity < 0) return fail(G4S_EINVAL, "g4s_forward_bin: bad sizes");
+    if (!geom_buffer || !img_buffer || !binning_buffer) return fail(G4S_EINVAL, "g4s_forward_bin: null buffer");
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     GeomView geom;
     ImageView img;
@@ -242,8 +241,23 @@ int g4s_forward_render(int P, int W, int H, const float* background, const void*
     ts.num_tiles = gx * gy; ts.capacity = capacity; ts.tile_offset = img.tile_offset; ts.tile_order = img.tile_order;
     ts.keys = bin.keys; ts.list = bin.list; ts.counters = img.counters;
     { StageTimer tm(ST_TILE_SORT, s); launch_tile_sort(ts, s); }
-    if ((rc = stage_check(debug, s, "tile_sort"))) return rc;
+    return stage_check(debug, s, "tile_sort");
+}
 
+// stage 2 of the render call: the blend
+int g4s_forward_blend(int P, int W, int H, const float* background, const void* geom_buffer, void* img_buffer,
+                      void* binning_buffer, int64_t capacity, float* out_color, float* out_others, void* stream, int debug) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P < 0 || W <= 0 || H <= 0 || capacity < 0) return fail(G4S_EINVAL, "g4s_forward_blend: bad sizes");
+    if (!geom_buffer || !img_buffer || !binning_buffer || !out_color || !out_others || !background)
+        return fail(G4S_EINVAL, "g4s_forward_blend: null buffer");
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    GeomView geom;
+    ImageView img;
+    BinView bin;
+    geom_layout(P, (char*)geom_buffer, &geom);
+    image_layout(W, H, (char*)img_buffer, &img);
+    bin_layout(capacity, (char*)binning_buffer, &bin);
     BlendFwdArgs ba;
     ba.W = W; ba.H = H; ba.grid_x = gx; ba.grid_y = gy; ba.capacity = capacity;
     ba.tile_offset = img.tile_offset; ba.tile_order = img.tile_order; ba.list = bin.list; ba.masks = bin.masks; ba.rec = geom.rec;
@@ -252,6 +266,15 @@ int g4s_forward_render(int P, int W, int H, const float* background, const void*
     ba.fast_math = g_fast_math.load(std::memory_order_relaxed);
     { StageTimer tm(ST_BLEND_FWD, s); launch_blend_fwd(ba, s); }
     return stage_check(debug, s, "blend_fwd");
+}
+
+int g4s_forward_render(int P, int W, int H, const float* background, const void* geom_buffer,
+                       void* img_buffer, void* binning_buffer, int64_t capacity, float* out_color,
+                       float* out_others, void* stream, int debug) {
+    if (!out_color || !out_others || !background) return fail(G4S_EINVAL, "g4s_forward_render: null buffer");
+    int rc = g4s_forward_bin(P, W, H, geom_buffer, img_buffer, binning_buffer, capacity, stream, debug);
+    if (rc != G4S_OK) return rc;
+    return g4s_forward_blend(P, W, H, background, geom_buffer, img_buffer, binning_buffer, capacity, out_color, out_others, stream, debug);
 }
 
 }  // extern "C"
@@ -301,7 +324,7 @@ static int backward_impl(int P, int D, int M, int W, int H, const float* backgro
     if ((rc = stage_check(debug, s, "blend_bwd"))) return rc;
 
     ProjectBwdArgs pb;
-    pb.P = P; pb.D = D; pb.M = M; pb.accumulate = accumulate_mask; pb.means3D = means3D; pb.shs = shs; pb.scales = scales; pb.rotations = rotations;
+    pb.P = P; pb.D = D; pb.M = M; pb.W = W; pb.H = H; pb.accumulate = accumulate_mask; pb.means3D = means3D; pb.shs = shs; pb.scales = scales; pb.rotations = rotations;
     pb.view = viewmatrix; pb.proj = projmatrix; pb.campos = cam_pos;
     pb.focal_y = H / (2.0f * tan_fovy);
     pb.focal_x = W / (2.0f * tan_fovx);

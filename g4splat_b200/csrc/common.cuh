@@ -30,11 +30,23 @@ constexpr float T_MIN = 0.0001f;
 constexpr int REC_F4 = 7;
 constexpr int REC_FLOATS = REC_F4 * 4;
 
-// ---- blend-stage gradient accumulator: 5 x float4 = 80 B per Gaussian -------------------------
-// a0 = dT[0..3]  a1 = dT[4..7]  a2 = (dT[8], dmean2D.x, dmean2D.y, dopacity)
-// a3 = (dcolor.r, dcolor.g, dcolor.b, dnormal.x)   a4 = (dnormal.y, dnormal.z, 0, 0)
-constexpr int ACC_F4 = 5;
+// ---- blend-stage gradient accumulator: 6 x float4 = 96 B per Gaussian (21 floats used) ----------------
+// The nine dT sums are carried as MOMENTS of q = dL/dp (CR/backward.cu:396-426) about a per-Gaussian origin (ox, oy),
+// which costs the blend kernel 17 scalar operations per lane instead of two cross products and three dot products
+// per pixel; project_bwd turns them into dT once per Gaussian:
+//   [0..2]  Q0 = sum q            [3..5]  Qx = sum (px - ox) q       [6..8]  Qy = sum (py - oy) q
+//   [9..11] Z  = sum (zs sx, zs sy, dL_dz)
+//   [12,13] dmean2D   [14] dopacity   [15..17] dcolor   [18..20] dnormal   [21..23] unused
+// with k_o = ox Tw - Tu, l_o = oy Tw - Tv (k, l of the origin pixel):
+//   dTu = Qy x Tw + Q0 x l_o      dTv = Tw x Qx + k_o x Q0      dTw = Z - (ox dTu + oy dTv + Qx x l_o + k_o x Qy)
+// (the dx dy terms cancel exactly).  The origin is the splat centre clamped into the image (moment_origin): every
+// pixel offset then stays below the image size, so the sums have the magnitudes of the reference's per-pixel
+// terms even for splats whose centre projects thousands of pixels off screen.
+constexpr int ACC_F4 = 6;
 constexpr int ACC_FLOATS = ACC_F4 * 4;
+constexpr int ACC_USED = 21;
+
+__host__ __device__ inline float moment_origin(float centre, float max_coord) { return fminf(fmaxf(centre, 0.0f), max_coord); }
 
 // ---- counters (device int32[8] inside the image buffer) ---------------------------------------
 enum { CNT_RENDERED = 0, CNT_MAXLEN = 1, CNT_VISIBLE = 2, CNT_PREFILTER_VIOLATION = 3, CNT_N = 8 };

@@ -91,7 +91,7 @@ void launch_blend_bwd(const BlendBwdArgs& a, cudaStream_t s);
 enum { ACC_MEANS3D = 1, ACC_SH = 2, ACC_OPACITY = 4, ACC_SCALES = 8, ACC_ROTATIONS = 16,
        ACC_MULTIMEM = 32 /* the accumulated outputs are NVSwitch multicast addresses: multimem.red */ };
 struct ProjectBwdArgs {
-    int P, D, M;
+    int P, D, M, W, H;
     int raw; const float* sh_rest; const float* opacities; const float* mip_filter; float* dL_dsh_rest;  // see ProjectArgs
     int accumulate;  // ACC_* bits: add into that output (visible rows only) instead of overwriting it
     const float* means3D; const float* shs; const float* scales; const float* rotations;

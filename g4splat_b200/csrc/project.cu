@@ -603,12 +603,30 @@ __global__ void __launch_bounds__(PB_THREADS) project_bwd_kernel(ProjectBwdArgs 
     if (visible) {
         // blend-stage accumulators
         const float4* acc = a.acc + (size_t)idx * ACC_F4;
-        const float4 a0 = acc[0], a1 = acc[1], a2 = acc[2], a3 = acc[3], a4 = acc[4];
-        float dT[3][3] = {{a0.x, a0.y, a0.z}, {a0.w, a1.x, a1.y}, {a1.z, a1.w, a2.x}};  // dT[j] = d/d(Tu,Tv,Tw)[j]
-        const float m2x = a2.y, m2y = a2.z;
-        const f3 dcol = mk3(a3.x, a3.y, a3.z);
-        const f3 dnrm = mk3(a3.w, a4.x, a4.y);
-        my[9] = a2.w;
+        const float4 a0 = acc[0], a1 = acc[1], a2 = acc[2], a3 = acc[3], a4 = acc[4], a5 = acc[5];
+        const float4* rec0 = a.geom.rec + (size_t)idx * REC_F4;
+        float dT[3][3];   // dT[j] = d/d(Tu,Tv,Tw)[j]
+        {
+            // moments of q about the Gaussian's moment origin -> dT (common.cuh, accumulator layout)
+            const float4 r1 = rec0[1], r2 = rec0[2], r3 = rec0[3];
+            const f3 rTu = mk3(r1.x, r1.y, r1.z), rTv = mk3(r1.w, r2.x, r2.y), rTw = mk3(r2.z, r2.w, r3.x);
+            const float ccx = moment_origin(r3.y, (float)(a.W - 1)), ccy = moment_origin(r3.z, (float)(a.H - 1));
+            const f3 kc = sub3(scale3(ccx, rTw), rTu), lc = sub3(scale3(ccy, rTw), rTv);
+            const f3 Q0 = mk3(a0.x, a0.y, a0.z), Qx = mk3(a0.w, a1.x, a1.y), Qy = mk3(a1.z, a1.w, a2.x), Z = mk3(a2.y, a2.z, a2.w);
+            const f3 c1 = cross3(Qy, rTw), c2 = cross3(Q0, lc), c3 = cross3(rTw, Qx), c4 = cross3(kc, Q0);
+            const f3 c5 = cross3(Qx, lc), c6 = cross3(kc, Qy);
+            const f3 dTu = mk3(c1.x + c2.x, c1.y + c2.y, c1.z + c2.z), dTv = mk3(c3.x + c4.x, c3.y + c4.y, c3.z + c4.z);
+            dT[0][0] = dTu.x; dT[0][1] = dTu.y; dT[0][2] = dTu.z;
+            dT[1][0] = dTv.x; dT[1][1] = dTv.y; dT[1][2] = dTv.z;
+            dT[2][0] = Z.x - (ccx * dTu.x + ccy * dTv.x + c5.x + c6.x);
+            dT[2][1] = Z.y - (ccx * dTu.y + ccy * dTv.y + c5.y + c6.y);
+            dT[2][2] = Z.z - (ccx * dTu.z + ccy * dTv.z + c5.z + c6.z);
+        }
+        const float raw_dT[9] = {dT[0][0], dT[0][1], dT[0][2], dT[1][0], dT[1][1], dT[1][2], dT[2][0], dT[2][1], dT[2][2]};
+        const float m2x = a3.x, m2y = a3.y;
+        const f3 dcol = mk3(a3.w, a4.x, a4.y);
+        const f3 dnrm = mk3(a4.z, a4.w, a5.x);
+        my[9] = a3.z;
         my[6] = dcol.x; my[7] = dcol.y; my[8] = dcol.z;
 
         // W, H as the reference rebuilds them in fp32 (CR/backward.cu:618-619)
@@ -681,10 +699,10 @@ __global__ void __launch_bounds__(PB_THREADS) project_bwd_kernel(ProjectBwdArgs 
             for (int j = 0; j < 3; j++) for (int c = 0; c < 3; c++) my[16 + 3 * j + c] = dT[j][c];
             proxy2 = dT[0][2]; proxy5 = dT[1][2];
         } else {
-            // the reference returns the raw blend-stage accumulator here
-            my[16] = a0.x; my[17] = a0.y; my[18] = a0.z; my[19] = a0.w; my[20] = a1.x; my[21] = a1.y;
-            my[22] = a1.z; my[23] = a1.w; my[24] = a2.x;
-            proxy2 = a0.z; proxy5 = a1.y;
+            // the reference returns the raw blend-stage accumulator here (dT before the low-pass update above)
+#pragma unroll
+            for (int j = 0; j < 9; j++) my[16 + j] = raw_dT[j];
+            proxy2 = raw_dT[2]; proxy5 = raw_dT[5];
             // dL_dM[c][k] = sum_j P[j][k] * dT[j][c]
             float dM[3][3];
 #pragma unroll

@@ -44,9 +44,14 @@ import torch.distributed as dist
 _ALIGN = 32   # floats: every block of the flat buffer starts on a 128-byte boundary
 
 
-def shard_views(num_views: int, world_size: int, rank: int) -> range:
-    """Contiguous block partition: the first (num_views % world_size) ranks get one extra view
-    (50 views on 4 ranks -> 13, 13, 12, 12)."""
+def shard_views(num_views: int, world_size: int, rank: int, strided: bool = False) -> range:
+    """The views of a step that `rank` renders; the first (num_views % world_size) ranks get one extra view
+    (50 views on 4 ranks -> 13, 13, 12, 12).  Default: contiguous blocks.  strided=True deals the views out like
+    cards (rank, rank + world_size, ...): neighbouring cameras of a capture cost about the same, so a contiguous
+    block gives a rank a correlated -- all cheap or all expensive -- set and the step waits for the unlucky rank;
+    dealing them out evens the per-rank sums (measured at 8 GPUs in DESIGN.md 5)."""
+    if strided:
+        return range(rank, num_views, world_size)
     base, extra = divmod(num_views, world_size)
     start = rank * base + min(rank, extra)
     return range(start, start + base + (1 if rank < extra else 0))

@@ -103,6 +103,14 @@ int g4s_forward_render(int P, int W, int H, const float* background,
                        const void* geom_buffer, void* img_buffer,
                        void* binning_buffer, int64_t capacity,
                        float* out_color, float* out_others, void* stream, int debug);
+/* The two halves of g4s_forward_render, for callers that run the front end of a view (plan + bin: every kernel
+ * before the blend, all latency-bound) on a side stream while the previous view's blend kernels occupy the main
+ * one (diff_surfel_rasterization.view_batch): g4s_forward_bin = scatter + per-tile sort, g4s_forward_blend = the
+ * blend.  g4s_forward_render(...) == g4s_forward_bin(...) followed by g4s_forward_blend(...) on the same stream. */
+int g4s_forward_bin(int P, int W, int H, const void* geom_buffer, void* img_buffer, void* binning_buffer,
+                    int64_t capacity, void* stream, int debug);
+int g4s_forward_blend(int P, int W, int H, const float* background, const void* geom_buffer, void* img_buffer,
+                      void* binning_buffer, int64_t capacity, float* out_color, float* out_others, void* stream, int debug);
 
 /* ---- backward ------------------------------------------------------------------------------ */
 /* Replaces CudaRasterizer::Rasterizer::backward (rasterizer_impl.cu:346-448) and the gradient

@@ -558,7 +558,8 @@ def test_gradient_sink_with_P_not_a_multiple_of_four(b200):
     b200.set_gradient_sink(None)
     for name, key in (("xyz", "dL_dmeans3D"), ("features", "dL_dsh"), ("opacity", "dL_dopacity"), ("scaling", "dL_dscales"),
                       ("rotation", "dL_drotations")):
-        assert Hh.parity(params[name].grad.cpu().numpy(), sum(s[key] for s in singles), 1e-4)["bad_frac"] == 0, name
+        # three views' worth of fp32 atomics in two different orders: the usual counted budget
+        assert Hh.parity(params[name].grad.cpu().numpy(), sum(s[key] for s in singles), 1e-4)["bad_frac"] <= GRAD_BUDGET, name
 
 
 def test_gradient_sink_entry_dies_with_its_parameter(b200):
@@ -638,21 +639,54 @@ def test_unsynchronised_forward_overflow_is_reported_before_its_backward(b200, o
     Hh.assert_parity(got, want, ("color", "allmap"), rtol=1e-4, max_bad_frac=FWD_BUDGET, what="after an overflowed call")
 
 
-def test_backward_kernel_variant_pair_matches_reference(tmp_path):
-    """G4S_BWD=pair (the 8x4-region backward that DESIGN.md 4 measures the default against) is selected once per process:
-    run two small side-by-side cases in a subprocess with the variable set."""
-    import subprocess
-    code = (
-        "import sys; sys.path.insert(0, 'tests'); import numpy as np; import helpers as Hh\n"
-        "import g4splat_b200.diff_surfel_rasterization as b200\n"
-        "from oracle import build_ref; from oracle.oracle import Oracle\n"
-        "ref = build_ref.import_reference(); o = Oracle('f32')\n"
-        "for name in ('ragged', 'c0_bg'):\n"
-        "    case = Hh.named_case(name, o)\n"
-        "    want = Hh.run_operator(ref, case); got = Hh.run_operator(b200, case)\n"
-        "    Hh.assert_parity(got, want, Hh.GRAD_KEYS, rtol=1e-4, max_bad_frac=2e-4, what=name)\n"
-        "    assert np.array_equal(got['color'], want['color'])\n"
-        "print('pair ok')\n")
-    env = dict(os.environ, G4S_BWD="pair")
-    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, env=env, timeout=600)
-    assert res.returncode == 0 and "pair ok" in res.stdout, res.stdout[-2000:] + res.stderr[-3000:]
+def test_view_batch_pipelining_matches_sequential(b200):
+    """64 interleaved views inside view_batch() (front end of every view on a high-priority side stream, ahead of the
+    previous view's blend / backward kernels): per-view outputs bit-identical to the sequential path, accumulated
+    gradients equal within the atomics' summation-order noise; a non-leaf input falls back to the ordinary path."""
+    import torch
+    from g4splat_b200 import synthetic as S
+    from g4splat_b200.view_parallel import ViewShardedGradSync
+    P, W, H, NV = 20_003, 320, 200, 64
+    sc = S.make_scene(P, 9)
+    dev = "cuda"
+    t = lambda a: torch.from_numpy(a).to(dev).requires_grad_(True)
+    params = {"xyz": t(sc["means3D"]), "features": t(sc["shs"]), "opacity": t(sc["opacities"]), "scaling": t(sc["scales"]),
+              "rotation": t(sc["rotations"])}
+    cams = S.make_cameras(7, W, H)
+    cases = [Hh.Case("v", sc, cams[(5 * k) % 7], grad_seed=3) for k in range(NV)]
+    settings = [Hh.make_settings(b200, c, dev) for c in cases]
+    gc, go = cases[0].upstream()
+    gc, go = torch.from_numpy(gc).to(dev), torch.from_numpy(go).to(dev)
+
+    def run(pipelined, scale_through_autograd=False):
+        sync = ViewShardedGradSync(params)
+        sync.bind(b200)
+        outs = []
+        ctx = b200.view_batch() if pipelined else __import__("contextlib").nullcontext()
+        with ctx as batch:
+            for k in range(NV):
+                m2d = torch.zeros_like(params["xyz"], requires_grad=True)
+                scales = params["scaling"] * 1.0 if scale_through_autograd else params["scaling"]
+                color, radii, allmap = b200.GaussianRasterizer(settings[k])(
+                    means3D=params["xyz"], means2D=m2d, opacities=params["opacity"], shs=params["features"], scales=scales,
+                    rotations=params["rotation"])
+                torch.autograd.backward([color, allmap], [gc, go])
+                sync.add_view_stats(m2d.grad, radii)
+                if k % 16 == 5:
+                    outs.append((color.detach().clone(), allmap.detach().clone(), radii.clone()))
+            prefetched = batch.prefetched if pipelined else 0
+        torch.cuda.synchronize()
+        flat = sync._store.clone()
+        b200.set_gradient_sink(None)
+        return flat, outs, prefetched
+
+    want, outs_w, _ = run(False)
+    got, outs_g, n = run(True)
+    assert n == NV
+    for (c0, a0, r0), (c1, a1, r1) in zip(outs_w, outs_g):
+        assert torch.equal(c0, c1) and torch.equal(a0, a1) and torch.equal(r0, r1)
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) <= 1e-5 * scale
+    got2, _, n2 = run(True, scale_through_autograd=True)       # a non-leaf input: no prefetching, same result
+    assert n2 == 0
+    assert float((got2 - want).abs().max()) <= 1e-5 * scale

@@ -24,7 +24,7 @@ bench)
 ncu)
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
      python bench.py --steps 2 --warmup 3 --views 2 --no-cpu-baseline --no-train-iteration --no-settle > gpurun_out/${TAG}_ncu_bench.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'blend_|project_|tile_|scatter' -s 72 -c 9 -f -o gpurun_out/${TAG}_prof \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'blend_|project_|tile_|scatter|acc_clear' -s 81 -c 10 -f -o gpurun_out/${TAG}_prof \
      python bench.py --steps 2 --warmup 3 --views 2 --no-cpu-baseline --no-train-iteration --no-settle > gpurun_out/${TAG}_ncu_full.log 2>&1
   # the caller-side rows: loss, post-processing, mip filter, raw-parameter projection
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:'photometric_(fwd|bwd)|surface_|mip_distance|project_.*true' -s 8 -c 8 -f -o gpurun_out/${TAG}_prof_next \

@@ -16,7 +16,8 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__registers_per_thread", "launch__shared_mem_per_block_static", "launch__shared_mem_per_block_dynamic",
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "smsp__inst_executed.sum",
         "smsp__thread_inst_executed_per_inst_executed.ratio", "lts__t_sector_hit_rate.pct",
-        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed_op_shared_atom.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed_op_shared_atom.sum",
         "smsp__inst_executed_op_global_red.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
 
 
@@ -77,7 +78,9 @@ def full(tag, out):
 
 STAGE_OF = {"project_fwd_kernel": "project_fwd", "tile_scan_kernel": "tile_scan", "scatter_kernel": "scatter",
             "tile_sort_kernel": "tile_sort", "tile_sort_warp_kernel": "tile_sort", "blend_fwd_kernel": "blend_fwd", "blend_fwd_tma_kernel": "blend_fwd",
-            "blend_bwd_kernel": "blend_bwd", "blend_fwd_warp_kernel": "blend_fwd", "blend_bwd_warp_kernel": "blend_bwd", "project_bwd_kernel": "project_bwd"}
+            "blend_bwd_kernel": "blend_bwd", "blend_fwd_warp_kernel": "blend_fwd", "blend_bwd_warp_kernel": "blend_bwd", "project_bwd_kernel": "project_bwd",
+            "blend_fwd_pair_kernel": "blend_fwd", "blend_bwd_tall_kernel": "blend_bwd", "blend_bwd_pair_kernel": "blend_bwd",
+            "acc_clear_kernel": "acc_clear"}
 
 
 def traffic(tag):
