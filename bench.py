@@ -172,17 +172,17 @@ def algorithmic_bytes(stage: str, P: int, V: int, R: int, N: int, T: int, K: int
     rec = 112 + 4 + 4 + 8 + 1                      # record + depth + ntiles + rect + clamp mask
     g = 12 + 12 * M + 4 + 8 + 16                   # gradient row: means3D, SH, opacity, scales, rotations
     if sink:
-        project_bwd = P * (4 + 12) + V * (80 + 48 + 40 + 12 * K + 2 * g)   # radii + dL_dmeans2D | acc, record, inputs, SH; RMW of the row
+        project_bwd = P * (4 + 12) + V * (96 + 48 + 40 + 12 * K + 2 * g)   # radii + dL_dmeans2D | acc, record, inputs, SH; RMW of the row
     else:
-        project_bwd = P * (4 + 12 + g) + V * (80 + 48 + 40 + 12 * K)
+        project_bwd = P * (4 + 12 + g) + V * (96 + 48 + 40 + 12 * K)
     return {
         "project_fwd": P * (40 + 4) + V * (12 * K + rec) + R * 4,
         "tile_scan": T * 16,
         "scatter": V * 16 + R * (8 + 4),
         "tile_sort": R * (8 + 4) + T * 8,
         "blend_fwd": R * (4 + 32) + V * 112 + N * 60 + T * 12,   # list + masks written; each visible record once; images
-        "acc_clear": P * 4 + V * 80,
-        "blend_bwd": R * (4 + 32) + V * (80 + 80) + N * 60 + T * 12,   # list + masks read; records; accumulator rows
+        "acc_clear": P * 4 + V * 96,
+        "blend_bwd": R * (4 + 32) + V * (80 + 96) + N * 60 + T * 12,   # list + masks read; records; 96-byte accumulator rows
         "project_bwd": project_bwd,
     }[stage]
 

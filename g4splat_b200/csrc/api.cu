@@ -433,6 +433,7 @@ int g4s_densify_gather(int P_new, int rest_width, const int* src_row, const uint
 int g4s_multimem_allreduce(float* sum_mc, int64_t n_floats, int* max_mc, int64_t n_ints, int rank, int world, void* stream) {
     if (n_floats < 0 || n_ints < 0 || world < 1 || rank < 0 || rank >= world || (n_floats & 3))
         return fail(G4S_EINVAL, "g4s_multimem_allreduce: bad sizes (n_floats must be a multiple of 4)");
+    if (n_floats == 0 && n_ints == 0) return G4S_OK;
     if ((n_floats && !sum_mc) || (n_ints && !max_mc)) return fail(G4S_EINVAL, "g4s_multimem_allreduce: null buffer");
     if ((reinterpret_cast<uintptr_t>(sum_mc) & 15) != 0) return fail(G4S_EINVAL, "g4s_multimem_allreduce: sum_mc must be 16-byte aligned");
     launch_multimem_allreduce(sum_mc, (size_t)n_floats, max_mc, (size_t)n_ints, rank, world, (cudaStream_t)stream);

@@ -302,12 +302,12 @@ class ViewShardedGradSync:
 
 
 def render_views_sharded(render_one, views: Sequence, sync: ViewShardedGradSync, rank: int, world_size: int,
-                         async_allreduce: bool = False):
-    """Runs `render_one(view) -> (loss, viewspace_points, radii)` for this rank's block of
-    `views`, back-propagates each loss (grads accumulate in the flat buffer), records the
-    densification statistics and all-reduces once.  Returns the local per-view losses."""
+                         async_allreduce: bool = False, strided: bool = False):
+    """Runs `render_one(view) -> (loss, viewspace_points, radii)` for this rank's share of
+    `views` (`shard_views`), back-propagates each loss (grads accumulate in the flat buffer), records the
+    densification statistics and combines the ranks' sums once.  Returns the local per-view losses."""
     losses = []
-    for i in shard_views(len(views), world_size, rank):
+    for i in shard_views(len(views), world_size, rank, strided=strided):
         loss, viewspace_points, radii = render_one(views[i])
         loss.backward()
         sync.add_view_stats(viewspace_points.grad, radii)

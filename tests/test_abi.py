@@ -58,3 +58,21 @@ def test_error_reporting_without_gpu():
     assert b"bad P/W/H" in lib.g4s_last_error()
     rc = lib.g4s_mark_visible(-5, None, None, None, None, None)
     assert rc == -1
+
+
+def test_round2_entry_points_validate_their_arguments_without_gpu():
+    from g4splat_b200 import _lib
+    lib = _lib.load()
+    assert lib.g4s_backward_scratch_bytes(1000) >= 1000 * 96          # 21 sums per Gaussian, 6 x float4
+    assert lib.g4s_set_fast_math(1) == 0 and lib.g4s_get_fast_math() == 1 and lib.g4s_set_fast_math(0) == 1
+    assert lib.g4s_multimem_allreduce(None, 6, None, 0, 0, 2, None) == -1 and b"multiple of 4" in lib.g4s_last_error()
+    assert lib.g4s_multimem_allreduce(None, 8, None, 0, 3, 2, None) == -1
+    assert lib.g4s_multimem_allreduce(None, 0, None, 0, 0, 1, None) == 0          # nothing to do
+    assert lib.g4s_densify_classify(-1, None, None, None, None, 0.0, 0.0, 0.0, 0.0, 2, None, None) == -1
+    assert lib.g4s_densify_classify(0, None, None, None, None, 0.0, 0.0, 0.0, 0.0, 2, None, None) == 0
+    assert lib.g4s_densify_gather(5, 45, None, None, None, None, 2, None, None, None) == -1
+    assert lib.g4s_normal2curv_forward(16, 16, None, None, None, None, None) == -1
+    assert lib.g4s_normal2curv_forward(0, 16, None, None, None, None, None) == 0
+    assert lib.g4s_depth_order_forward(0, 4, None, None, None, 1.0, 1, 0, 20.0, None, None, None) == -1
+    assert lib.g4s_forward_bin(-1, 16, 16, None, None, None, 0, None, 0) == -1
+    assert lib.g4s_forward_blend(1, 16, 16, None, None, None, None, 0, None, None, None, 0) == -1

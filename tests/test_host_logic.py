@@ -216,3 +216,49 @@ def test_capacity_policy_buckets():
     grown = pol.guess(0, 1_000_000)
     pol.observe(0, 100_000)                                      # four-fold smaller: shrinks
     assert pol.guess(0, 1_000_000) < grown
+
+
+# ---------------------------------------------------------------------------------- round 2 host logic
+def test_shard_views_partitions_every_view_exactly_once():
+    from g4splat_b200.view_parallel import shard_views
+    for n, world in ((50, 4), (64, 8), (7, 3), (3, 8), (0, 2)):
+        for strided in (False, True):
+            seen = sorted(i for r in range(world) for i in shard_views(n, world, r, strided=strided))
+            assert seen == list(range(n)), (n, world, strided)
+            sizes = [len(shard_views(n, world, r, strided=strided)) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+    assert [len(shard_views(50, 4, r)) for r in range(4)] == [13, 13, 12, 12]        # c3 on 4 GPUs
+    assert list(shard_views(16, 8, 3, strided=True)) == [3, 11]
+
+
+def test_flat_gradient_buffer_layout_pads_blocks_and_follows_rebind():
+    """Every block of the view-sharded gradient buffer starts on a 128-byte boundary whatever P is (the kernels' 16-byte
+    reductions need aligned rows), p.grad aliases its block, and rebind() lays the buffer out again when P changes."""
+    import torch
+    from g4splat_b200.view_parallel import ViewShardedGradSync
+
+    def params(P):
+        mk = lambda *shape: torch.zeros(*shape, requires_grad=True)
+        return {"xyz": mk(P, 3), "f_dc": mk(P, 1, 3), "f_rest": mk(P, 15, 3), "opacity": mk(P, 1), "scaling": mk(P, 2), "rotation": mk(P, 4)}
+
+    p = params(1003)
+    sync = ViewShardedGradSync(p, transport="nccl", use_native=False)
+    base = sync._store.data_ptr()
+    for k, v in p.items():
+        assert (sync._views[k].data_ptr() - base) % 128 == 0, k
+        assert v.grad.data_ptr() == sync._views[k].data_ptr() and v.grad.shape == v.shape
+    assert (sync._accum.data_ptr() - base) % 128 == 0 and (sync.max_radii.data_ptr() - base) % 128 == 0
+    assert sync.max_radii.dtype == torch.int32 and sync.max_radii.numel() == 1003
+    assert sync.flat.numel() % 4 == 0 and sync.bytes_per_step == sync.flat.numel() * 4 + 1003 * 4
+    # statistics in plain torch (the reference arm of the benchmark uses exactly this path)
+    g = torch.zeros(1003, 3); g[5] = torch.tensor([3.0, 4.0, 9.0])
+    r = torch.zeros(1003, dtype=torch.int32); r[5] = 7; r[6] = 2
+    sync.add_view_stats(g, r)
+    assert float(sync.xyz_gradient_accum[5]) == 5.0 and float(sync.denom[5]) == 1.0 and float(sync.denom[6]) == 1.0
+    assert int(sync.max_radii[5]) == 7 and float(sync.denom.sum()) == 2.0
+    q = params(1501)
+    sync.rebind(q)
+    assert sync.P == 1501 and all(v.grad is not None and v.grad.shape == v.shape for v in q.values())
+    assert float(sync._store.abs().sum()) == 0.0
+    with __import__("pytest").raises(ValueError):
+        ViewShardedGradSync(p, transport="carrier-pigeon", use_native=False)

@@ -3,6 +3,8 @@ operator sequences (the torch restatements under oracle/ run on CUDA tensors = t
 reference launches):
   * photometric loss (L1 + SSIM, forward + backward) at 3x1080x1920          -- loss_utils.py, train:382-383
   * compute_mip_filter for 1.0 M Gaussians and 64 cameras                    -- gaussian_model.py:388-434
+  * normal2curv, compute_depth_order_loss at 1080p                           -- matcha/dm_utils/rendering.py, dm_regularization/depth.py
+  * densify_and_prune on 1.0 M Gaussians with Adam moments                   -- gaussian_model.py:528-647
 
     python tests/tools/bench_trainer_ops.py [--iters 30]      # prints one JSON line per row
 """
@@ -143,13 +145,103 @@ def bench_activations(iters):
                               "incl. the 192 B/Gaussian cat of the SH tensors) against in-register activations"}))
 
 
+def bench_regularizers(iters):
+    """normal2curv and the depth-order loss at 1080p, forward + backward, against the reference's torch sequences
+    (oracle/regularizers_oracle.py restates matcha/dm_utils/rendering.py:392-406 and matcha/dm_regularization/depth.py:142-222)."""
+    from g4splat_b200 import regularization as R
+    from oracle import regularizers_oracle as RO
+    H, W = 1080, 1920
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    normal = torch.randn(3, H, W, device="cuda", generator=gen)
+    mask = torch.ones(1, H, W, device="cuda")
+    depth = 1.0 + 4.0 * torch.rand(1, H, W, device="cuda", generator=gen)
+    prior = depth * 0.8 + 0.3 * torch.randn(1, H, W, device="cuda", generator=gen)
+    max_shift = round(0.05 * max(H, W))
+
+    def curv(fn):
+        def run():
+            n = normal.clone().requires_grad_(True)
+            fn(n, mask).mean().backward()
+        return run
+
+    def order(fused):
+        def run():
+            d = depth.clone().requires_grad_(True)
+            if fused:
+                loss = R.compute_depth_order_loss(d, prior, scene_extent=3.3, log_space=True)
+            else:
+                shifts = torch.randint(-max_shift, max_shift + 1, (H * W, 2), device="cuda")
+                loss = RO.depth_order_loss(d, prior, shifts, 3.3, True, True, 20., "mean")
+            loss.backward()
+        return run
+
+    for row, f, r in (("normal2curv forward + backward, 3x1080x1920", curv(R.normal2curv), curv(RO.normal2curv)),
+                      ("compute_depth_order_loss forward + backward, 1080x1920 (incl. the randint draw)", order(True), order(False))):
+        ms_f, ms_r = timed(f, iters), timed(r, iters)
+        print(json.dumps({"row": row, "fused_ms": ms_f, "reference_torch_ops_ms": ms_r, "speedup": ms_r / ms_f, "iters": iters}))
+
+
+def bench_densify(iters):
+    """densify_and_prune on 1.0 M Gaussians with Adam moments, against the reference's sequence (oracle/densify_oracle.py
+    restates scene/gaussian_model.py:528-647 on plain tensors: the same torch kernels the reference launches)."""
+    import types
+    from g4splat_b200.gaussian_model import densify_and_prune
+    from g4splat_b200 import synthetic as S
+    from oracle import densify_oracle as DO
+    P = 1_000_000
+    sc = S.make_scene(P, 2)
+    rng = np.random.default_rng(3)
+    op = np.clip(sc["opacities"], 1e-4, 1 - 1e-4)
+    raw = {"xyz": sc["means3D"], "f_dc": sc["shs"][:, :1], "f_rest": sc["shs"][:, 1:], "opacity": np.log(op / (1 - op)),
+           "scaling": np.log(sc["scales"]), "rotation": sc["rotations"]}
+    raw = {k: torch.tensor(np.ascontiguousarray(v, dtype=np.float32), device="cuda") for k, v in raw.items()}
+    accum = torch.tensor(np.float32(np.abs(rng.normal(scale=0.0004, size=(P, 1))) * 5), device="cuda")
+    denom = torch.full((P, 1), 5.0, device="cuda")
+    attr = {"xyz": "_xyz", "f_dc": "_features_dc", "f_rest": "_features_rest", "opacity": "_opacity", "scaling": "_scaling", "rotation": "_rotation"}
+    sizes = {}
+
+    def fused():
+        model = types.SimpleNamespace(percent_dense=0.01, xyz_gradient_accum=accum.clone(), denom=denom.clone(),
+                                      max_radii2D=torch.zeros(P, device="cuda"))
+        groups = []
+        for k, a in attr.items():
+            p_ = torch.nn.Parameter(raw[k].clone())
+            setattr(model, a, p_)
+            groups.append({"params": [p_], "lr": 1e-3, "name": k})
+        model.optimizer = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+        for g in groups:
+            model.optimizer.state[g["params"][0]] = {"step": torch.tensor(3.0), "exp_avg": torch.zeros_like(g["params"][0]),
+                                                     "exp_avg_sq": torch.zeros_like(g["params"][0])}
+        sizes["fused"] = densify_and_prune(model, 0.0002, 0.05, 5.0, 20)
+
+    def reference():
+        params = {k: v.clone() for k, v in raw.items()}
+        moments = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in raw.items()}
+        grads = accum / denom
+        sel = (grads.squeeze() >= 0.0002) & (torch.exp(params["scaling"]).max(dim=1).values > 0.01 * 5.0)
+        stds = torch.exp(params["scaling"][sel]).repeat(2, 1)
+        stds = torch.cat([stds, 0 * torch.ones_like(stds[:, :1])], dim=-1)
+        samples = torch.normal(mean=torch.zeros_like(stds), std=stds)
+        p_, _ = DO.densify_and_prune(params, moments, accum.clone(), denom.clone(), 0.01, 0.0002, 0.05, 5.0, 20, samples)
+        sizes["ref"] = int(p_["xyz"].shape[0])
+
+    # both arms pay the same clones of the inputs (six parameters + moments); the difference is the densification itself
+    ms_f, ms_r = timed(fused, max(3, iters // 3)), timed(reference, max(3, iters // 3))
+    print(json.dumps({"row": f"densify_and_prune, {P} Gaussians with Adam moments ({sizes.get('fused')} afterwards; setup clones included in both arms)",
+                      "fused_ms": ms_f, "reference_torch_ops_ms": ms_r, "speedup": ms_r / ms_f, "P_after_fused": sizes.get("fused"),
+                      "P_after_reference": sizes.get("ref"), "iters": max(3, iters // 3)}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=30)
+    ap.add_argument("--only", default="")
     args = ap.parse_args()
-    bench_loss(args.iters)
-    bench_mip(args.iters)
-    bench_activations(args.iters)
+    rows = {"loss": bench_loss, "mip": bench_mip, "activations": bench_activations, "regularizers": bench_regularizers,
+            "densify": bench_densify}
+    for name, fn in rows.items():
+        if not args.only or name in args.only.split(","):
+            fn(args.iters)
 
 
 if __name__ == "__main__":
