@@ -571,41 +571,48 @@ __global__ void decode_ranges_kernel(int T, const uint32_t* tile_offset, uint32_
     ranges[2 * i] = tile_offset[i];
     ranges[2 * i + 1] = tile_offset[i + 1];
 }
-// One CTA per tile, one warp per 8x4 region, the same walk as the backward: positions below the warp's last
-// contributor whose box meets the region carry a valid forward mask.
+// One CTA per tile, one warp per 8x8 block (two 8x4 regions), the same walk as blend_bwd_tall_kernel: an entry is
+// replayed when either region's forward mask is non-zero, and then costs 64 pair slots (two pixels per lane).
+//   out[0] pairs blended   out[1] sum over pixels of the last contributor's list position   out[2] pair slots (256 per entry)
+//   out[3] longest list    out[4] pair slots the backward issues                             out[5] (block, entry) hits
 __global__ void pair_stats_kernel(int W, int H, int grid_x, const uint32_t* tile_offset, const uint32_t* list,
                                   const uint32_t* masks, const float4* rec, const uint32_t* n_contrib,
                                   unsigned long long* out) {
+    (void)list; (void)rec;
     const int tile = blockIdx.x, ty = tile / grid_x, tx = tile - ty * grid_x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bx = tx * TILE + (warp & 1) * REGION_W, by = ty * TILE + (warp >> 1) * REGION_H;
-    const int px = bx + (lane & 7), py = by + (lane >> 3);
-    const float rx0 = (float)bx, ry0 = (float)by;
-    const float rx1 = (float)min(bx + REGION_W - 1, W - 1), ry1 = (float)min(by + REGION_H - 1, H - 1);
+    const int sub = threadIdx.x >> 5, lane = threadIdx.x & 31;          // 4 warps: 8x8 blocks
+    const int wU = 4 * (sub >> 1) + (sub & 1), wL = wU + 2;
+    const int px = tx * TILE + (wU & 1) * REGION_W + (lane & 7);
+    const int pyU = ty * TILE + (wU >> 1) * REGION_H + (lane >> 3), pyL = pyU + REGION_H;
     const uint32_t off = tile_offset[tile];
     const int n = (int)(tile_offset[tile + 1] - off);
-    int last = (px < W && py < H) ? (int)n_contrib[(size_t)W * py + px] : 0;
-    unsigned long long walked = last, blended = 0, issued = 0;
-    int warp_last = last;
-    for (int o = 16; o; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(~0u, warp_last, o));
-    for (int pos = lane; pos < min(n, warp_last); pos += 32) {
-        const float4 bb = rec[(size_t)list[off + pos] * REC_F4];
-        if (bb.x <= rx1 && bb.z >= rx0 && bb.y <= ry1 && bb.w >= ry0) {
-            const uint32_t m = masks[(size_t)off * 8 + (size_t)warp * n + pos];
-            blended += __popc(m);
-            issued += m ? 32 : 0;
-        }
+    const int lastU = (px < W && pyU < H) ? (int)n_contrib[(size_t)W * pyU + px] : 0;
+    const int lastL = (px < W && pyL < H) ? (int)n_contrib[(size_t)W * pyL + px] : 0;
+    unsigned long long walked = (unsigned long long)lastU + lastL, blended = 0, issued = 0, hits = 0;
+    int liveU = lastU, liveL = lastL;
+    for (int o = 16; o; o >>= 1) {
+        liveU = max(liveU, __shfl_xor_sync(~0u, liveU, o));
+        liveL = max(liveL, __shfl_xor_sync(~0u, liveL, o));
+    }
+    liveU = min(liveU, n); liveL = min(liveL, n);
+    for (int pos = lane; pos < max(liveU, liveL); pos += 32) {
+        const uint32_t mU = pos < liveU ? masks[(size_t)off * 8 + (size_t)wU * n + pos] : 0u;
+        const uint32_t mL = pos < liveL ? masks[(size_t)off * 8 + (size_t)wL * n + pos] : 0u;
+        blended += __popc(mU) + __popc(mL);
+        if (mU | mL) { issued += 64; hits += 1; }
     }
     for (int o = 16; o; o >>= 1) {
         blended += __shfl_xor_sync(~0u, blended, o);
         walked += __shfl_xor_sync(~0u, walked, o);
         issued += __shfl_xor_sync(~0u, issued, o);
+        hits += __shfl_xor_sync(~0u, hits, o);
     }
     if (lane == 0) {
         atomicAdd(out + 0, blended);
         atomicAdd(out + 1, walked);
         atomicAdd(out + 4, issued);
-        if (warp == 0) {
+        atomicAdd(out + 5, hits);
+        if (sub == 0) {
             atomicAdd(out + 2, (unsigned long long)n * (TILE * TILE));
             atomicMax(out + 3, (unsigned long long)n);
         }
@@ -653,7 +660,7 @@ int g4s_debug_pair_stats(int W, int H, const void* geom_buffer, int P, const voi
     const int gx = (W + TILE - 1) / TILE, T = gx * ((H + TILE - 1) / TILE);
     int rc;
     if ((rc = check_cuda(cudaMemsetAsync(stats, 0, 8 * sizeof(uint64_t), s), "clear pair stats"))) return rc;
-    pair_stats_kernel<<<T, TILE_PIX, 0, s>>>(W, H, gx, img.tile_offset, bin.list, bin.masks, geom.rec, img.n_contrib,
+    pair_stats_kernel<<<T, 128, 0, s>>>(W, H, gx, img.tile_offset, bin.list, bin.masks, geom.rec, img.n_contrib,
                                              (unsigned long long*)stats);
     return stage_check(false, s, "pair_stats");
 }

@@ -742,7 +742,7 @@ def debug_pair_stats(rendered: torch.Tensor) -> dict:
     geom, binning, img = saved[-3:]
     rs = ctx.raster_settings
     P = int(saved[1].shape[0])
-    keys = ("pairs_blended", "pairs_walked", "pair_slots", "longest_tile_list", "pair_evals_bwd")
+    keys = ("pairs_blended", "pairs_walked", "pair_slots", "longest_tile_list", "pair_evals_bwd", "block_entry_hits")
     if P == 0:
         return dict.fromkeys(keys, 0)
     lib = _lib.load()
@@ -751,7 +751,7 @@ def debug_pair_stats(rendered: torch.Tensor) -> dict:
         _lib.check(lib.g4s_debug_pair_stats(int(rs.image_width), int(rs.image_height), geom.data_ptr(), P, img.data_ptr(),
                                             binning.data_ptr(), int(ctx.capacity), stats.data_ptr(),
                                             torch.cuda.current_stream(geom.device).cuda_stream))
-    return dict(zip(keys, (int(v) for v in stats[:5].tolist())))
+    return dict(zip(keys, (int(v) for v in stats[:6].tolist())))
 
 
 class GaussianRasterizationSettings(NamedTuple):
