@@ -65,7 +65,7 @@ def load_peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled every 100 ms while the timed region runs.
+    """SM clock and throttle reasons sampled every 40 ms while the timed region runs (the region is ~0.3 s).
 
     Source: the NVML calls behind `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*`
     made from a thread of this process (nvidia_ml_py); G4S_BENCH_CLOCKS=smi spawns nvidia-smi itself
@@ -128,7 +128,7 @@ class ClockSampler:
                 self.samples.append((float(sm), float(mx), {n for n, b in bits.items() if r & b}))
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.04)
 
     def _pump(self):
         for line in self.proc.stdout:
