@@ -21,6 +21,7 @@ then reported by the next call).
 """
 from __future__ import annotations
 
+import collections.abc
 import contextlib
 import os
 import threading
@@ -128,7 +129,7 @@ def _state(dev: torch.device) -> _DeviceState:
     return st
 
 
-class _LastCounts(dict):
+class _LastCounts(collections.abc.Mapping):
     """(num_rendered, longest tile list, visible Gaussians) of the most recent forward on the CURRENT device
     whose plan the host has waited for; benchmarks read it to size the algorithmic-bytes model."""
 
@@ -143,12 +144,6 @@ class _LastCounts(dict):
 
     def __len__(self):
         return len(self._d())
-
-    def keys(self):
-        return self._d().keys()
-
-    def items(self):
-        return self._d().items()
 
     def __repr__(self):
         return repr(self._d())
