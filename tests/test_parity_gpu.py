@@ -690,3 +690,18 @@ def test_view_batch_pipelining_matches_sequential(b200):
     got2, _, n2 = run(True, scale_through_autograd=True)       # a non-leaf input: no prefetching, same result
     assert n2 == 0
     assert float((got2 - want).abs().max()) <= 1e-5 * scale
+
+
+@pytest.mark.parametrize("W,H", [(17, 9), (100, 37), (8, 8), (641, 359), (33, 130)])
+def test_odd_resolutions_match_reference(W, H, b200, reference):
+    """Image sizes that are not multiples of the 16-pixel tile, the 8x8 backward block or the 8x4 forward region (down to
+    a single block): partial tiles, blocks whose lower region is outside the image, one-tile images."""
+    from g4splat_b200 import synthetic as S
+    sc = S.make_scene(3_000, 40 + W)
+    cam = S.make_cameras(3, W, H)[1]
+    case = Hh.Case(f"odd_{W}x{H}", sc, cam, grad_seed=4)
+    want = Hh.run_operator(reference, case)
+    got = Hh.run_operator(b200, case)
+    assert Hh.radii_mismatch(got["radii"], want["radii"]) == 0
+    assert np.array_equal(got["color"], want["color"]) and np.array_equal(got["allmap"], want["allmap"])
+    Hh.assert_parity(got, want, Hh.GRAD_KEYS, rtol=1e-4, max_bad_frac=GRAD_BUDGET, what=f"{W}x{H} backward vs reference")
