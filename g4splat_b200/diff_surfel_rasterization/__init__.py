@@ -102,6 +102,49 @@ def host_trace_summary() -> dict:
 _RING = 256             # pinned count slots per device; a slot is reused only after _RING further forwards
 
 
+class _ScratchSet:
+    """One set of forward scratch buffers (radii, geometry, image, binning) owned by the pipelined path of view_batch().
+    The torch caching allocator cannot serve that path: buffers written on the side stream and consumed on the main one
+    need `record_stream`, which defers their reuse until the main stream has caught up, so with the host a view or two
+    ahead every forward ends in a fresh cudaMalloc (measured: 0.8 ms of host time per view).  The sets are allocated once,
+    grown when a view needs more, and recycled explicitly: `released` is recorded on the consuming stream by the backward
+    of the view that used the set (or when its autograd context dies), and the side stream waits for it before reuse."""
+    __slots__ = ("radii", "geom", "img", "binning", "busy", "released", "generation")
+
+    def __init__(self):
+        self.radii = self.geom = self.img = self.binning = None
+        self.busy = False
+        self.released = None
+        self.generation = 0
+
+
+class _Lease:
+    """Held by the autograd context of a pipelined forward: gives the scratch set back when the backward has been
+    enqueued, or when the context is dropped without one."""
+
+    def __init__(self, sset, dev):
+        self.sset, self.dev, self.generation, self.done = sset, dev, sset.generation, False
+
+    def check(self):
+        if self.done or self.generation != self.sset.generation:
+            raise RuntimeError("g4s rasterizer: the scratch buffers of this view_batch() forward have been recycled "
+                               "(a second backward through the same graph is not supported inside view_batch)")
+
+    def release(self):
+        if not self.done:
+            self.done = True
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.dev))
+            self.sset.released = ev
+            self.sset.busy = False
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
+
 class _DeviceState:
     """Everything the shim remembers between calls, per CUDA device (one process may drive several devices
     from several threads): the pinned ring the plan stage reports its counts into, the overflow checks a
@@ -114,6 +157,8 @@ class _DeviceState:
         self.pending_overflow = []   # (event, pinned counts, capacity) of G4S_SYNC=none calls not yet checked
         self.last_counts = {"num_rendered": 0, "max_tile_list": 0, "visible": 0}
         self.batch = None            # _ViewBatch while a view_batch() block is open on this device
+        self.pipe_sets = [_ScratchSet() for _ in range(3)]   # persistent scratch of the pipelined path, used round-robin
+        self.pipe_next = 0
 
 
 _states = {}
@@ -316,7 +361,9 @@ def _plan_and_render(dev, P, W, H, bg, rs, plan, prefetchable=False):
         t_begin = time.perf_counter()
     batch = st.batch if (prefetchable and not debug) else None
     if batch is not None:
-        return _plan_and_render_pipelined(dev, dev_index, st, batch, P, W, H, bg, rs, plan)
+        out = _plan_and_render_pipelined(dev, dev_index, st, batch, P, W, H, bg, rs, plan)
+        if out is not None:
+            return out
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev)
         sp = stream.cuda_stream
@@ -365,12 +412,20 @@ def _plan_and_render(dev, P, W, H, bg, rs, plan, prefetchable=False):
             cap = _capacity.bucket(num_rendered + 65536)  # the speculative launch was a no-op: re-issue
         if debug and rs.prefiltered and int(counts[3]) != 0:
             raise RuntimeError("Point is filtered although prefiltered is set. This shouldn't happen!")
-    return color, others, radii, geom, binning, img, cap, num_rendered, counts
+    return color, others, radii, geom, binning, img, cap, num_rendered, counts, None
 
 
 def _plan_and_render_pipelined(dev, dev_index, st, batch, P, W, H, bg, rs, plan):
-    """view_batch(): plan + scatter + sort on the batch's side stream, the blend on the current one."""
+    """view_batch(): plan + scatter + sort on the batch's side stream into a recycled scratch set, the blend on the
+    current stream.  Returns None when no scratch set is free (the caller then takes the ordinary path)."""
+    sset = st.pipe_sets[st.pipe_next]
+    if sset.busy:
+        return None
+    st.pipe_next = (st.pipe_next + 1) % len(st.pipe_sets)
     f32 = dict(dtype=torch.float32, device=dev)
+    if _HOST_TRACE:
+        import time
+        t_begin = time.perf_counter()
     with torch.cuda.device(dev):
         main = torch.cuda.current_stream(dev)
         side = batch.side
@@ -380,20 +435,33 @@ def _plan_and_render_pipelined(dev, dev_index, st, batch, P, W, H, bg, rs, plan)
         if mode == "none":
             _check_pending(st, dev_index)
         cap = _capacity.guess(dev_index, P)
-        with torch.cuda.stream(side):
-            radii = torch.empty((P,), dtype=torch.int32, device=dev)
-            geom = torch.empty((_LIB.g4s_geom_bytes(P),), dtype=torch.uint8, device=dev)
-            img = torch.empty((_LIB.g4s_image_bytes(W, H),), dtype=torch.uint8, device=dev)
-            binning = torch.empty((_LIB.g4s_binning_bytes(cap),), dtype=torch.uint8, device=dev)
-            _lib.check(plan(radii, geom, img, counts, side.cuda_stream))
-            planned = torch.cuda.Event()
-            planned.record(side)
-            _lib.check(_LIB.g4s_forward_bin(P, W, H, geom.data_ptr(), img.data_ptr(), binning.data_ptr(), cap, side.cuda_stream, 0))
-            binned = torch.cuda.Event()
-            binned.record(side)
-        for t in (radii, geom, img, binning):
-            t.record_stream(main)        # allocated on the side stream, consumed (and kept for the backward) on this one
+        need = (P, _LIB.g4s_geom_bytes(P), _LIB.g4s_image_bytes(W, H), _LIB.g4s_binning_bytes(cap))
+        if sset.geom is None or sset.radii.numel() < need[0] or sset.geom.numel() < need[1] or sset.img.numel() < need[2] \
+                or sset.binning.numel() < need[3]:
+            # (re)allocate from the main stream's pool; the side stream must not touch the new blocks before everything
+            # already queued on the main stream -- the possible previous owners of that memory -- has run
+            sset.radii = torch.empty((need[0],), dtype=torch.int32, device=dev)
+            sset.geom = torch.empty((need[1],), dtype=torch.uint8, device=dev)
+            sset.img = torch.empty((need[2],), dtype=torch.uint8, device=dev)
+            sset.binning = torch.empty((need[3],), dtype=torch.uint8, device=dev)
+            fence = torch.cuda.Event()
+            fence.record(main)
+            side.wait_event(fence)
+        if sset.released is not None:
+            side.wait_event(sset.released)       # the view that used this set last has finished its backward
+        sset.busy = True
+        sset.generation += 1
+        lease = _Lease(sset, dev)
+        radii_s, geom, img, binning = sset.radii, sset.geom, sset.img, sset.binning
+        sp = side.cuda_stream
+        _lib.check(plan(radii_s, geom, img, counts, sp))
+        planned = torch.cuda.Event()
+        planned.record(side)
+        _lib.check(_LIB.g4s_forward_bin(P, W, H, geom.data_ptr(), img.data_ptr(), binning.data_ptr(), cap, sp, 0))
+        binned = torch.cuda.Event()
+        binned.record(side)
         main.wait_event(binned)
+        radii = radii_s[:P].clone()              # the caller's tensor: the set's copy is recycled
         color = torch.empty((NUM_CHANNELS, H, W), **f32)
         others = torch.empty((_OTHERS, H, W), **f32)
         _lib.check(_LIB.g4s_forward_blend(P, W, H, bg.data_ptr(), geom.data_ptr(), img.data_ptr(), binning.data_ptr(), cap,
@@ -401,8 +469,14 @@ def _plan_and_render_pipelined(dev, dev_index, st, batch, P, W, H, bg, rs, plan)
         batch.prefetched += 1
         if mode == "none":
             st.pending_overflow.append((planned, counts, cap))
-            return color, others, radii, geom, binning, img, cap, -1, counts
+            return color, others, radii, geom, binning, img, cap, -1, counts, lease
+        if _HOST_TRACE:
+            t_wait = time.perf_counter()
         planned.synchronize()            # the side stream ran ahead: usually already complete
+        if _HOST_TRACE:
+            t_done = time.perf_counter()
+            _host_times["fwd_launch"].append(t_wait - t_begin)
+            _host_times["fwd_wait"].append(t_done - t_wait)
         num_rendered = int(counts[0])
         st.last_counts.update(num_rendered=num_rendered, max_tile_list=int(counts[1]), visible=int(counts[2]))
         _capacity.observe(dev_index, num_rendered)
@@ -413,7 +487,7 @@ def _plan_and_render_pipelined(dev, dev_index, st, batch, P, W, H, bg, rs, plan)
             binning = torch.empty((_LIB.g4s_binning_bytes(cap),), dtype=torch.uint8, device=dev)
             _lib.check(_LIB.g4s_forward_render(P, W, H, bg.data_ptr(), geom.data_ptr(), img.data_ptr(), binning.data_ptr(), cap,
                                                color.data_ptr(), others.data_ptr(), main.cuda_stream, 0))
-    return color, others, radii, geom, binning, img, cap, num_rendered, counts
+    return color, others, radii, geom, binning, img, cap, num_rendered, counts, lease
 
 
 def _leaf_or_constant(*tensors) -> bool:
@@ -480,6 +554,7 @@ class _RasterizeGaussians(torch.autograd.Function):
 
         f32 = dict(dtype=torch.float32, device=dev)
         num_rendered = 0
+        ctx.lease = None
         if P == 0:
             # reference: kernels skipped, zero images returned (rasterize_points.cu:85-99)
             color = torch.zeros((NUM_CHANNELS, H, W), **f32)
@@ -500,16 +575,17 @@ class _RasterizeGaussians(torch.autograd.Function):
                                       cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height,
                                       rs.image_width, sh, rs.sh_degree, rs.campos, rs.prefiltered, rs.debug))
                 try:
-                    color, others, radii, geom, binning, img, cap, num_rendered, counts = _plan_and_render(dev, P, W, H, bg, rs, plan)
+                    color, others, radii, geom, binning, img, cap, num_rendered, counts, lease = _plan_and_render(dev, P, W, H, bg, rs, plan)
                 except Exception as ex:
                     _dump_snapshot("snapshot_fw.dump", cpu_args)
                     print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
                     raise ex
             else:
-                color, others, radii, geom, binning, img, cap, num_rendered, counts = _plan_and_render(
+                color, others, radii, geom, binning, img, cap, num_rendered, counts, lease = _plan_and_render(
                     dev, P, W, H, bg, rs, plan,
                     prefetchable=_leaf_or_constant(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp))
             ctx.counts = counts
+            ctx.lease = lease
 
         ctx.sinks, ctx.sink_flags = _resolve_sinks({"means3D": means3D, "sh": sh, "opacities": opacities,
                                                     "scales": scales, "rotations": rotations})
@@ -530,6 +606,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         colors_c, means3D_c, scales_c, rots_c, cov_c, radii, sh_c, geom, binning, img = ctx.saved_tensors
         dev = means3D_c.device
         _settle_pending(dev)
+        lease = getattr(ctx, "lease", None)
+        if lease is not None:
+            lease.check()
         P = int(means3D_c.size(0))
         M = ctx.M
         H, W = int(rs.image_height), int(rs.image_width)
@@ -592,6 +671,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                         raise ex
                 else:
                     call()
+        if lease is not None:
+            lease.release()      # the scratch set of this view may be recycled once the kernels above have run
         if _HOST_TRACE:
             _host_times["bwd"].append(time.perf_counter() - t_begin)
         # same order as the reference (RAST/diff_surfel_rasterization/__init__.py:144-154)
@@ -643,6 +724,7 @@ class _RasterizeGaussianModel(torch.autograd.Function):
         campos = _f32c(rs.campos, "campos")
         f32 = dict(dtype=torch.float32, device=dev)
         num_rendered, cap = 0, 0
+        ctx.lease = None
         if P == 0:
             color = torch.zeros((NUM_CHANNELS, H, W), **f32)
             others = torch.zeros((_OTHERS, H, W), **f32)
@@ -655,10 +737,11 @@ class _RasterizeGaussianModel(torch.autograd.Function):
                     scal_c.data_ptr(), float(rs.scale_modifier), rot_c.data_ptr(), _ptr(mip_c), _ptr(view), _ptr(proj),
                     _ptr(campos), float(rs.tanfovx), float(rs.tanfovy), int(bool(rs.prefiltered)), radii.data_ptr(),
                     geom.data_ptr(), img.data_ptr(), counts.data_ptr(), sp, int(bool(rs.debug)))
-            color, others, radii, geom, binning, img, cap, num_rendered, counts = _plan_and_render(
+            color, others, radii, geom, binning, img, cap, num_rendered, counts, lease = _plan_and_render(
                 dev, P, W, H, bg, rs, plan,
                 prefetchable=_leaf_or_constant(xyz, features_dc, features_rest, opacity, scaling, rotation, mip_filter))
             ctx.counts = counts
+            ctx.lease = lease
         # the SH gradient is one kernel output mode for both tensors: they are sunk together or not at all
         ctx.sinks, ctx.sink_flags = _resolve_sinks({"means3D": xyz, "sh": features_dc, "sh_rest": features_rest,
                                                     "opacities": opacity, "scales": scaling, "rotations": rotation})
@@ -685,6 +768,9 @@ class _RasterizeGaussianModel(torch.autograd.Function):
         f32 = dict(dtype=torch.float32, device=dev)
         alloc = torch.zeros if P == 0 else torch.empty  # every element is written by the kernels
         _settle_pending(dev)
+        lease = getattr(ctx, "lease", None)
+        if lease is not None:
+            lease.check()
         sinks = ctx.sinks or {}
         acc_mask = 0
 
@@ -722,6 +808,8 @@ class _RasterizeGaussianModel(torch.autograd.Function):
                     int(ctx.capacity), img.data_ptr(), g_color.data_ptr(), g_others.data_ptr(), k_xyz,
                     g_means2D.data_ptr(), k_dc, k_rest, k_op, k_sc,
                     k_rot, acc_mask, scratch.data_ptr(), sp, int(bool(rs.debug))))
+        if lease is not None:
+            lease.release()
         return g_xyz, g_means2D, g_dc, g_rest, g_op, g_sc, g_rot, None, None
 
 
