@@ -432,6 +432,39 @@ def time_train_iteration(wl: "Workload", mod, fused: bool, views: int, device):
     return e0.elapsed_time(e1) / views
 
 
+def time_operator(wl: "Workload", mod, device, views: int = 20, warm: int = 3):
+    """SURVEY.md 8(d) timing protocol, per view through the plain operator API (no gradient sink, dense gradients
+    returned to autograd as the reference does): 3 warm-up + 20 timed views, CUDA events on the current stream, the
+    forward and the backward timed separately and together, output allocation included; median / p10 / p90 in ms.
+    The views run one at a time with a host synchronise between them, so each number is an operator LATENCY (launch
+    latency and the mid-forward count read-back included), not the throughput of the step loop above."""
+    import torch
+    rows = []
+    for i in range(warm + views):
+        vid = (5 * i + 1) % wl.ring
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        for p_ in wl.params.values():
+            p_.grad = None          # autograd keeps the returned tensors as they are: no accumulation pass inside the timing
+        torch.cuda.synchronize(device)
+        e0.record()
+        color, radii, allmap, means2D = wl.rasterize(mod, vid)
+        e1.record()
+        torch.autograd.backward([color, allmap], [wl.g_color, wl.g_allmap])
+        e2.record()
+        torch.cuda.synchronize(device)
+        if i >= warm:
+            rows.append((e0.elapsed_time(e1), e1.elapsed_time(e2), e0.elapsed_time(e2)))
+        del color, radii, allmap, means2D
+    for p_ in wl.params.values():
+        p_.grad = None
+    a = np.array(rows)
+    q = lambda col: {"median": float(np.median(a[:, col])), "p10": float(np.percentile(a[:, col], 10)),
+                     "p90": float(np.percentile(a[:, col], 90))}
+    return {"unit": "ms per view", "views": views, "warmup": warm, "forward": q(0), "backward": q(1), "forward_backward": q(2),
+            "gaussians_per_s_median": wl.P / (float(np.median(a[:, 2])) * 1e-3),
+            "what": "plain operator API, one view at a time with a host synchronise in between (SURVEY.md 8d protocol)"}
+
+
 def op_counts_snapshot(mod):
     lc = getattr(mod, "last_counts", None)
     return dict(lc) if lc else None
@@ -685,6 +718,11 @@ def main():
                     "arm": "this repository's fused kernels for every row" if fused else
                            "the reference rasterizer with the reference's torch operator sequences around it"}
 
+    op_timing = None
+    if world == 1 and not args.no_train_iteration:
+        op_timing = time_operator(wl, mod, device)
+        sync.zero()                       # re-attaches the flat gradient buffer that time_operator detached
+
     check = None
     if dist_on and lib is not None and not args.no_check:
         check = allreduce_self_check(wl, mod, sync, device)
@@ -729,6 +767,8 @@ def main():
             "gpu_launches": launches, "clocks": clk}
     if train_it is not None:
         line["train_iteration"] = train_it
+    if op_timing is not None:
+        line["operator_timing"] = op_timing
     if fast is not None:
         line["fast_math"] = fast
     if check is not None:

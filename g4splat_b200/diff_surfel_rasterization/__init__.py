@@ -210,8 +210,7 @@ def _pinned_counts(st: _DeviceState) -> torch.Tensor:
         st.ring_next = (st.ring_next + 1) % _RING
         wrapped = st.ring_next == 0
     if wrapped and st.pending_overflow:
-        torch.cuda.synchronize()
-        _check_pending(st)
+        _check_pending(st, wait=True)     # the slots about to be reused still carry unchecked counts
     return slot
 
 
