@@ -12,6 +12,7 @@ namespace g4s {
 
 constexpr int SCAN_THREADS = 1024;
 constexpr int ORDER_BUCKETS = 64;
+constexpr int LONG_BUCKET_END = 47;   // bucket_of(c) < 47  <=>  c >= 256 (lg = 8, lower half -> 64 - 2 - 16 = 46)
 
 // Single-CTA exclusive scan over the tile counts + bucketed longest-first tile order.
 __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(TileScanArgs a) {
@@ -72,6 +73,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(TileScanArgs a)
         }
         bucket_base[2 * lane] = bi - bsum;
         bucket_base[2 * lane + 1] = bi - bsum + b0;
+        // tiles with >= 256 entries fill the buckets below LONG_BUCKET_END: their number is that bucket's base, i.e. the
+        // prefix of tile_order the long-list sort has to look at
+        if (2 * lane + 1 == LONG_BUCKET_END) a.counters[CNT_LONG_TILES] = (int32_t)(bi - bsum + b0);
     }
     __syncthreads();
     uint32_t run = warp_sums[warp] + (incl - local);
@@ -94,8 +98,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(TileScanArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
-constexpr int SORT_THREADS = 256;
-constexpr int SORT_SMEM_KEYS = 4096;  // 32 KB of shared memory; longer lists sort in global memory
+// The per-tile sort is ONE launch of 128-thread CTAs with two roles (tile_sort_kernel below):
+//   * lists of up to 256 entries (nearly all of them: the mean list holds ~160) -- one warp per list, in registers;
+//   * longer lists -- one CTA per list: 256-key register chunks merged through shared memory up to 1024 entries, the
+//     shared-memory network below up to 2048, the same network in global memory (L2-resident) above.
+// tile_scan_kernel orders the tiles longest first and counts the long ones, so the long-list CTAs (first in the grid,
+// persistent over that prefix of tile_order) start before the short-list CTAs and nothing is launched per empty slot.
+// History (ms per view at c2): one 256-thread CTA per tile for the long lists + a second launch for the warps 0.064
+// (8160 CTAs, seven in eight of which looked at their tile and left); this kernel 0.048.
 
 // Bitonic sorting network in its "all ascending" form: the first step of every merge compares
 // element i of the lower half with its mirror in the upper half, the remaining steps are the
@@ -109,7 +119,7 @@ __device__ __forceinline__ void bitonic_sort_ascending(KeyArray keys, int n) {
     // all block sizes are powers of two: index arithmetic is shifts and masks, no division
     for (int lk = 1; lk <= log_m; lk++) {          // k = 1 << lk
         const int k = 1 << lk, hk = k >> 1;
-        for (int i = threadIdx.x; i < half; i += SORT_THREADS) {
+        for (int i = threadIdx.x; i < half; i += blockDim.x) {
             const int within = i & (hk - 1);
             const int blk_base = (i >> (lk - 1)) << lk;
             const int lo = blk_base + within, hi = blk_base + k - 1 - within;
@@ -121,7 +131,7 @@ __device__ __forceinline__ void bitonic_sort_ascending(KeyArray keys, int n) {
         __syncthreads();
         for (int lj = lk - 2; lj >= 0; lj--) {     // j = 1 << lj
             const int j = 1 << lj;
-            for (int i = threadIdx.x; i < half; i += SORT_THREADS) {
+            for (int i = threadIdx.x; i < half; i += blockDim.x) {
                 const int lo = ((i >> lj) << (lj + 1)) | (i & (j - 1)), hi = lo + j;
                 if (hi < n) {
                     const unsigned long long x = keys[lo], y = keys[hi];
@@ -133,12 +143,13 @@ __device__ __forceinline__ void bitonic_sort_ascending(KeyArray keys, int n) {
     }
 }
 
-// Lists of up to WARP_SORT_MAX = 256 entries (nearly all of them: the mean list holds ~160) are sorted by ONE
-// warp in registers: element e = r * 32 + lane lives in register r of its lane, compare-exchange
-// partners at distance < 32 are reached with a shuffle, larger distances are other registers of the
-// same lane.  No shared memory, no block barrier; eight tiles per CTA.  Padding keys are all-ones
-// (greater than any depth<<32|index key), so they stay behind the n real entries.
-constexpr int WARP_SORT_MAX = 256;   // (512 with 16 registers per lane was measured: the long lists then form a single-warp tail, 0.063 -> 0.078 ms)
+// Lists of up to WARP_SORT_MAX = 256 entries are sorted by ONE warp in registers: element e = r * 32 + lane lives in
+// register r of its lane, compare-exchange partners at distance < 32 are reached with a shuffle, larger distances are
+// other registers of the same lane.  No shared memory, no block barrier.  Padding keys are all-ones (greater than
+// any depth<<32|index key), so they stay behind the n real entries.
+constexpr int WARP_SORT_MAX = 256;   // (512 with 16 registers per lane was measured: the long lists then form a single-warp tail, 0.063 -> 0.078 ms.
+                                     //  A "blocked" layout e = lane * NREG + r halves the shuffle steps and gained 1.7 us of 48: the kernel is bound
+                                     //  by its ~20 M warp instructions and the dependent loads, not by the shuffle rate; not kept.)
 
 template <int NREG>
 __device__ __forceinline__ void warp_bitonic_sort(unsigned long long (&key)[NREG], int lane) {
@@ -191,9 +202,128 @@ __device__ __forceinline__ void warp_sort_tile(const unsigned long long* __restr
     }
 }
 
-__global__ void __launch_bounds__(SORT_THREADS) tile_sort_warp_kernel(TileSortArgs a) {
+// ---- one launch for both list classes ----------------------------------------------------------------------
+// Ascending merge tail of the all-ascending network: the half-cleaners at distances 128 .. 1 inside a 256-key chunk
+// held as 8 registers per lane (element e = r * 32 + lane).
+__device__ __forceinline__ void warp_merge_tail(unsigned long long (&key)[8], int lane) {
+#pragma unroll
+    for (int jr = 4; jr > 0; jr >>= 1) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            if ((r & jr) == 0) {
+                const unsigned long long x = key[r], y = key[r | jr];
+                const bool swap = x > y;
+                key[r] = swap ? y : x;
+                key[r | jr] = swap ? x : y;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const bool lower = (lane & j) == 0;
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const unsigned long long x = key[r];
+            const unsigned long long y = __shfl_xor_sync(0xffffffffu, x, j);
+            key[r] = lower ? (x < y ? x : y) : (x > y ? x : y);
+        }
+    }
+}
+
+// Lists of 257 .. 1024 entries: warp w sorts chunk w (256 keys) in registers, then the chunks are merged by the
+// all-ascending network -- only the steps whose partner lies in ANOTHER chunk (the mirror step of a merge and its
+// half-cleaners at distances >= 256) go through shared memory, one block barrier each (two buffers, used alternately);
+// everything below distance 256 is the register tail above.  A 794-entry list takes 3 barriers instead of the 55 of
+// the shared-memory network.  Chunks that lie wholly above n are virtual +inf keys: an exchange with one never changes
+// the real chunk (it is the lower side), so it is skipped.
+constexpr int HYBRID_MAX = 1024;          // four warps x 256 keys
+__device__ __forceinline__ void hybrid_sort_tile(const unsigned long long* __restrict__ gk, uint32_t* __restrict__ out, int n,
+                                                 unsigned long long* s_buf /* [2][HYBRID_MAX] */) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int C = (n + 255) >> 8;
+    unsigned long long key[8];
+    if (w < C) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int e = w * 256 + r * 32 + lane;
+            key[r] = e < n ? gk[e] : ~0ull;
+        }
+        warp_bitonic_sort<8>(key, lane);
+    }
+    int phase = 0;
+    for (int kc = 2; kc < 2 * C; kc <<= 1) {                 // chunks per merged block
+        // step 0: the mirror step; steps 1..: half-cleaners at chunk distances kc / 4, kc / 8, .. 1
+        for (int step = 0;; step++) {
+            const bool mirror = step == 0;
+            const int dist = mirror ? 0 : (kc >> (step + 1));
+            if (!mirror && dist == 0) break;
+            unsigned long long* buf = s_buf + phase * HYBRID_MAX;
+            phase ^= 1;
+            if (w < C) {
+#pragma unroll
+                for (int r = 0; r < 8; r++) buf[w * 256 + r * 32 + lane] = key[r];
+            }
+            __syncthreads();
+            if (w < C) {
+                const int cb = w & (kc - 1);
+                const int partner = mirror ? (w - cb + (kc - 1 - cb)) : (w ^ dist);
+                const bool lower = mirror ? (cb < (kc >> 1)) : ((w & dist) == 0);
+                if (partner < C) {
+#pragma unroll
+                    for (int r = 0; r < 8; r++) {
+                        const int e = r * 32 + lane;
+                        const unsigned long long y = buf[partner * 256 + (mirror ? 255 - e : e)];
+                        const unsigned long long x = key[r];
+                        key[r] = lower ? (x < y ? x : y) : (x > y ? x : y);
+                    }
+                }
+            }
+        }
+        if (w < C) warp_merge_tail(key, lane);
+    }
+    if (w < C) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int e = w * 256 + r * 32 + lane;
+            if (e < n) out[e] = (uint32_t)key[r];
+        }
+    }
+}
+
+constexpr int PS_THREADS = 128;            // four warps: one long list (<= 1024 entries by register chunks) or four short ones
+constexpr int PS_SMEM_KEYS = 2 * HYBRID_MAX;
+constexpr int LONG_CTAS = 2072;            // 14 x 148: more than the SMs hold at once (10 per SM at 48 registers); 1024 .. 4096 measured within 3 us
+__global__ void __launch_bounds__(PS_THREADS) tile_sort_kernel(TileSortArgs a) {
     if ((int64_t)a.counters[CNT_RENDERED] > a.capacity) return;
-    const int slot = blockIdx.x * (SORT_THREADS / 32) + (threadIdx.x >> 5);
+    __shared__ unsigned long long s_keys[PS_SMEM_KEYS];
+    // long lists first: tile_order starts with them, longest first, and with ~1500 CTAs resident each normally gets
+    // its own CTA; the short-list CTAs fill the SMs as those retire
+    const int b = (int)blockIdx.x;
+    if (b < LONG_CTAS) {
+        const int n_long = a.counters[CNT_LONG_TILES];
+        for (int i = b; i < n_long; i += LONG_CTAS) {
+            const int tile = (int)a.tile_order[i];
+            const uint32_t off = a.tile_offset[tile];
+            const int n = (int)(a.tile_offset[tile + 1] - off);
+            if (n <= WARP_SORT_MAX) continue;              // exactly 256: a warp below takes it
+            unsigned long long* gk = a.keys + off;
+            if (n <= HYBRID_MAX) {
+                hybrid_sort_tile(gk, a.list + off, n, s_keys);
+            } else if (n <= PS_SMEM_KEYS) {
+                for (int j = threadIdx.x; j < n; j += PS_THREADS) s_keys[j] = gk[j];
+                __syncthreads();
+                bitonic_sort_ascending(s_keys, n);
+                for (int j = threadIdx.x; j < n; j += PS_THREADS) a.list[off + j] = (uint32_t)s_keys[j];
+            } else {
+                __syncthreads();
+                bitonic_sort_ascending(gk, n);
+                for (int j = threadIdx.x; j < n; j += PS_THREADS) a.list[off + j] = (uint32_t)gk[j];
+            }
+            __syncthreads();                               // the shared buffers are reused by the next tile
+        }
+        return;
+    }
+    const int slot = (b - LONG_CTAS) * (PS_THREADS / 32) + (threadIdx.x >> 5);
     if (slot >= a.num_tiles) return;
     const int lane = threadIdx.x & 31;
     const int tile = (int)a.tile_order[slot];
@@ -208,39 +338,14 @@ __global__ void __launch_bounds__(SORT_THREADS) tile_sort_warp_kernel(TileSortAr
     else warp_sort_tile<8>(gk, out, n, lane);
 }
 
-// Lists longer than WARP_SORT_MAX: one CTA per tile, in shared memory.
-__global__ void __launch_bounds__(SORT_THREADS) tile_sort_kernel(TileSortArgs a) {
-    if ((int64_t)a.counters[CNT_RENDERED] > a.capacity) return;
-    extern __shared__ unsigned long long s_keys[];
-    const int tile = (int)a.tile_order[blockIdx.x];
-    const uint32_t off = a.tile_offset[tile];
-    const int n = (int)(a.tile_offset[tile + 1] - off);
-    if (n <= WARP_SORT_MAX) return;
-    unsigned long long* gk = a.keys + off;
-    if (n <= SORT_SMEM_KEYS) {
-        for (int i = threadIdx.x; i < n; i += SORT_THREADS) s_keys[i] = gk[i];
-        __syncthreads();
-        bitonic_sort_ascending(s_keys, n);
-        for (int i = threadIdx.x; i < n; i += SORT_THREADS) a.list[off + i] = (uint32_t)s_keys[i];
-    } else {
-        // rare: very long list -- same network, in place in global memory (L2-resident)
-        __syncthreads();
-        bitonic_sort_ascending(gk, n);
-        for (int i = threadIdx.x; i < n; i += SORT_THREADS) a.list[off + i] = (uint32_t)gk[i];
-    }
-}
-
 void launch_tile_scan(const TileScanArgs& a, cudaStream_t s) {
     tile_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(a);
     count_launch();
 }
 void launch_tile_sort(const TileSortArgs& a, cudaStream_t s) {
     if (a.num_tiles <= 0) return;
-    // long lists first (they sit at the front of tile_order), then everything else by warps
-    tile_sort_kernel<<<a.num_tiles, SORT_THREADS, SORT_SMEM_KEYS * sizeof(unsigned long long), s>>>(a);
-    count_launch();
-    const int warps_per_cta = SORT_THREADS / 32;
-    tile_sort_warp_kernel<<<(a.num_tiles + warps_per_cta - 1) / warps_per_cta, SORT_THREADS, 0, s>>>(a);
+    const int short_ctas = (a.num_tiles + PS_THREADS / 32 - 1) / (PS_THREADS / 32);
+    tile_sort_kernel<<<LONG_CTAS + short_ctas, PS_THREADS, 0, s>>>(a);
     count_launch();
 }
 

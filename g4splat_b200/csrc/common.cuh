@@ -49,7 +49,7 @@ constexpr int ACC_USED = 21;
 __host__ __device__ inline float moment_origin(float centre, float max_coord) { return fminf(fmaxf(centre, 0.0f), max_coord); }
 
 // ---- counters (device int32[8] inside the image buffer) ---------------------------------------
-enum { CNT_RENDERED = 0, CNT_MAXLEN = 1, CNT_VISIBLE = 2, CNT_PREFILTER_VIOLATION = 3, CNT_N = 8 };
+enum { CNT_RENDERED = 0, CNT_MAXLEN = 1, CNT_VISIBLE = 2, CNT_PREFILTER_VIOLATION = 3, CNT_LONG_TILES = 4, CNT_N = 8 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

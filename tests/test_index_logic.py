@@ -1,5 +1,5 @@
 """Index logic of two kernels restated in Python and checked exhaustively / on random inputs (no GPU):
-the register bitonic network of `tile_sort_warp_kernel` and the owner search of `scatter_kernel`
+the register bitonic network and the chunk merge of `tile_sort_kernel` and the owner search of `scatter_kernel`
 (g4splat_b200/csrc/binning.cu, project.cu).  The GPU parity tests check the kernels themselves; these keep
 the reasoning behind their index arithmetic executable."""
 import random
@@ -46,6 +46,62 @@ def test_warp_bitonic_network_sorts_every_length():
     # equal depths: (depth << 32 | index) keys are distinct, ties in depth resolve by index
     keys = [(7 << 32) | i for i in rng.sample(range(1000), 200)]
     assert warp_bitonic(keys, 8) == sorted(keys)
+
+
+def hybrid_sort(keys):
+    """binning.cu: hybrid_sort_tile -- 256-key chunks sorted in registers (one warp each), merged by the all-ascending
+    network: the mirror step and the half-cleaners at chunk distances go through shared memory, the distances below
+    256 are warp_merge_tail.  Chunks wholly above n are virtual +inf and are never exchanged with."""
+    pad = (1 << 64) - 1
+    n = len(keys)
+    C = (n + 255) >> 8
+    ch = [[keys[w * 256 + e] if w * 256 + e < n else pad for e in range(256)] for w in range(C)]
+    ch = [warp_bitonic([k for k in c], 8) for c in ch]
+
+    def merge_tail(c):
+        c = list(c)
+        j = 128
+        while j > 0:
+            for lo in range(256):
+                if (lo & j) == 0 and c[lo] > c[lo + j]:
+                    c[lo], c[lo + j] = c[lo + j], c[lo]
+            j >>= 1
+        return c
+
+    kc = 2
+    while kc < 2 * C:
+        step = 0
+        while True:
+            mirror = step == 0
+            dist = 0 if mirror else (kc >> (step + 1))
+            if not mirror and dist == 0:
+                break
+            buf = [list(c) for c in ch]                   # the shared-memory copy every warp reads its partner from
+            for w in range(C):
+                cb = w & (kc - 1)
+                partner = (w - cb + (kc - 1 - cb)) if mirror else (w ^ dist)
+                lower = (cb < (kc >> 1)) if mirror else ((w & dist) == 0)
+                if partner < C:
+                    for e in range(256):
+                        y = buf[partner][255 - e if mirror else e]
+                        ch[w][e] = min(ch[w][e], y) if lower else max(ch[w][e], y)
+            step += 1
+        ch = [merge_tail(c) for c in ch]
+        kc <<= 1
+    return [ch[e >> 8][e & 255] for e in range(n)]
+
+
+def test_hybrid_chunk_merge_sorts_every_chunk_count():
+    rng = random.Random(2)
+    for n in (257, 300, 511, 512, 513, 700, 768, 769, 794, 1000, 1023, 1024):
+        keys = [rng.getrandbits(60) for _ in range(n)]
+        assert hybrid_sort(keys) == sorted(keys), n
+        keys = [(rng.randrange(5) << 32) | i for i in rng.sample(range(5000), n)]     # heavy depth ties
+        assert hybrid_sort(keys) == sorted(keys), n
+    # the network itself is valid up to eight chunks (the kernel uses four)
+    for n in (1025, 1537, 2048):
+        keys = [rng.getrandbits(60) for _ in range(n)]
+        assert hybrid_sort(keys) == sorted(keys), n
 
 
 def scatter_owner(excl, i):

@@ -363,6 +363,25 @@ def test_long_tile_lists_global_sort_fallback(b200, reference, oracle32):
     Hh.assert_parity(got, want, Hh.GRAD_KEYS, rtol=1e-4, max_bad_frac=GRAD_BUDGET, what="dense backward vs reference")
 
 
+def test_every_sort_path_orders_like_the_reference(b200, reference):
+    """The per-tile sort picks its method by list length: one warp in registers up to 256 entries, register chunks merged
+    through shared memory up to 2048, the shared-memory network up to 4096, global memory above.  Dense scenes of
+    growing size put lists into every class; the forward must stay bit-identical (a single misplaced entry changes
+    the blend order)."""
+    classes = set()
+    for P in (700, 1500, 3000, 6000, 10000):
+        case = _dense_case(P, 128, 96, 50 + P, 0.25, 0.03)
+        want = Hh.run_operator(reference, case)
+        got = Hh.run_operator(b200, case)
+        longest = int(b200.last_counts["max_tile_list"])
+        classes.add(int(np.searchsorted([256, 512, 1024, 2048, 4096], longest, side="left")))
+        print("P", P, "longest list", longest)
+        assert np.array_equal(got["allmap"], want["allmap"]), (P, longest)
+        Hh.assert_parity(got, want, ("color",), rtol=1e-6, what=f"dense P={P} forward vs reference")
+        Hh.assert_parity(got, want, Hh.GRAD_KEYS, rtol=1e-4, max_bad_frac=GRAD_BUDGET, what=f"dense P={P} backward vs reference")
+    assert len(classes) >= 4, classes
+
+
 def test_saturating_splats_early_termination(b200, reference):
     """Opaque splats: pixels saturate (T < 1e-4) after a few entries, warps and whole tiles stop early;
     the contribution masks of entries that were never visited must not be consulted."""
