@@ -169,10 +169,11 @@ def algorithmic_bytes(stage: str, P: int, V: int, R: int, N: int, T: int, K: int
     every output written once, every (Gaussian, tile) instance written once and read once.
     sink: project_bwd adds the rows of VISIBLE Gaussians into the multi-view sum (read-modify-write) and writes
     no dense per-view gradient except dL_dmeans2D; otherwise it writes every row of every gradient tensor."""
-    rec = 112 + 4 + 4 + 8 + 1                      # record + depth + ntiles + rect + clamp mask
+    rec = 112 + 4 + 4 + 8 + 1 + 4                  # record + depth + ntiles + rect + clamp mask + visible-list entry
     g = 12 + 12 * M + 4 + 8 + 16                   # gradient row: means3D, SH, opacity, scales, rotations
     if sink:
-        project_bwd = P * (4 + 12) + V * (96 + 48 + 40 + 12 * K + 2 * g)   # radii + dL_dmeans2D | acc, record, inputs, SH; RMW of the row
+        # dL_dmeans2D cleared and its visible rows stored | list entry, radius, acc, record, inputs, SH; RMW of the row
+        project_bwd = P * 12 + V * (4 + 4 + 12 + 96 + 48 + 40 + 12 * K + 2 * g)
     else:
         project_bwd = P * (4 + 12 + g) + V * (96 + 48 + 40 + 12 * K)
     return {

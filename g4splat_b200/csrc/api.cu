@@ -328,7 +328,7 @@ static int backward_impl(int P, int D, int M, int W, int H, const float* backgro
     pb.view = viewmatrix; pb.proj = projmatrix; pb.campos = cam_pos;
     pb.focal_y = H / (2.0f * tan_fovy);
     pb.focal_x = W / (2.0f * tan_fovx);
-    pb.tan_fovx = tan_fovx; pb.tan_fovy = tan_fovy; pb.radii = radii; pb.geom = geom; pb.acc = acc;
+    pb.tan_fovx = tan_fovx; pb.tan_fovy = tan_fovy; pb.radii = radii; pb.geom = geom; pb.acc = acc; pb.counters = img.counters;
     pb.dL_dmeans3D = dL_dmeans3D; pb.dL_dmeans2D = dL_dmeans2D; pb.dL_dsh = (M > 0 && shs) ? dL_dsh : nullptr;
     pb.dL_dcolors = dL_dcolors; pb.dL_dopacity = dL_dopacity; pb.dL_dscales = dL_dscales; pb.dL_drots = dL_drotations;
     pb.dL_dtransMat = dL_dtransMat;

@@ -60,6 +60,7 @@ struct GeomView {
     uint32_t* ntiles;   // [P] tiles touched after exact culling
     ushort4* rect;      // [P] culled tile rectangle (x0, y0, x1, y1), x1/y1 exclusive
     uint8_t* clamped;   // [P] bit c set when SH colour channel c was clamped at 0
+    uint32_t* visible_list;   // [P] ids of the Gaussians with radii > 0 (counters[CNT_VISIBLE] of them), in no particular order
 };
 __host__ __device__ inline size_t geom_layout(int P, char* base, GeomView* v) {
     size_t off = 0;
@@ -70,12 +71,14 @@ __host__ __device__ inline size_t geom_layout(int P, char* base, GeomView* v) {
     size_t o_nt = take(n * sizeof(uint32_t));
     size_t o_rect = take(n * sizeof(ushort4));
     size_t o_cl = take(n);
+    size_t o_vl = take(n * sizeof(uint32_t));
     if (v) {
         v->rec = (float4*)(base + o_rec);
         v->depth = (float*)(base + o_depth);
         v->ntiles = (uint32_t*)(base + o_nt);
         v->rect = (ushort4*)(base + o_rect);
         v->clamped = (uint8_t*)(base + o_cl);
+        v->visible_list = (uint32_t*)(base + o_vl);
     }
     return off;
 }

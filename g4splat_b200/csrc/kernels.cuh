@@ -100,6 +100,7 @@ struct ProjectBwdArgs {
     const int* radii;
     GeomView geom;
     const float4* acc;
+    const int32_t* counters;   // [CNT_N] of the forward (CNT_VISIBLE sizes geom.visible_list)
     float* dL_dmeans3D; float* dL_dmeans2D; float* dL_dsh; float* dL_dcolors; float* dL_dopacity;
     float* dL_dscales; float* dL_drots; float* dL_dtransMat;
 };

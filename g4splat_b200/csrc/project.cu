@@ -382,7 +382,12 @@ __global__ void __launch_bounds__(PF_THREADS, 4) project_fwd_kernel(ProjectArgs 
         s_geo[19][slot] = (uint32_t)idx;
     }
     __syncthreads();
-    if (threadIdx.x == 0 && total > 0) atomicAdd(&a.counters[CNT_VISIBLE], total);
+    // the survivors also go into the view's list of visible Gaussians (the backward projection walks it): every warp
+    // reserves room for its share of the compacted survivors
+    const int warp_share = min(32, max(0, total - warp * 32));
+    int list_base = 0;
+    if (lane == 0 && warp_share > 0) list_base = atomicAdd(&a.counters[CNT_VISIBLE], warp_share);
+    list_base = __shfl_sync(0xffffffffu, list_base, 0);
 
     // ---- phase 2: thread t takes the t-th survivor of the CTA ---------------------------------------
     const int t = threadIdx.x;
@@ -402,6 +407,7 @@ __global__ void __launch_bounds__(PF_THREADS, 4) project_fwd_kernel(ProjectArgs 
         const uint32_t r0 = s_geo[17][t], r1 = s_geo[18][t];
         g.rx0 = (int)(r0 & 0xffffu); g.ry0 = (int)(r0 >> 16); g.rx1 = (int)(r1 & 0xffffu); g.ry1 = (int)(r1 >> 16);
         id2 = (int)s_geo[19][t];
+        a.geom.visible_list[list_base + lane] = (uint32_t)id2;
         project_appearance<RAW>(a, id2, g, o);
     }
     const int gx = a.grid_x;
@@ -499,23 +505,45 @@ __global__ void __launch_bounds__(256) scatter_kernel(ScatterArgs a) {
 // ---------------------------------------------------------------------------------------------
 // Backward of the SH colour (CR/backward.cu:20-139): writes dL_dsh[idx][k] for k < (D+1)^2 and
 // zeros above, returns the view-direction term to add to dL_dmean3D.
-__device__ __forceinline__ f3 sh_backward(int deg, int M, const float* __restrict__ shr /* coefficients 1.. */, f3 dir_orig,
+// `row4` (may be null): the Gaussian's whole [16][3] coefficient row when it is 16-byte aligned -- the usual case, 192-byte
+// rows of a torch tensor -- read with twelve 128-bit loads instead of 45 scalar ones (a scalar load of a warp touches
+// one cache line per lane: the loads of this function were a third of the kernel's L1 wavefronts).
+__device__ __forceinline__ f3 sh_backward(int deg, int M, const float* __restrict__ shr /* coefficients 1.. */,
+                                          const float4* __restrict__ row4, f3 dir_orig,
                                           uint8_t clamp_mask, f3 dL_dcolor, float* __restrict__ dsh) {
+    float row[48];   // row[3 k + c] = coefficient k, channel c; filled per degree block, compile-time indices only
+    auto load_block = [&](int q0, int q1) {
+        if (row4 != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 12; q++) {
+                if (q >= q0 && q < q1) {
+                    const float4 v = row4[q];
+                    row[4 * q] = v.x; row[4 * q + 1] = v.y; row[4 * q + 2] = v.z; row[4 * q + 3] = v.w;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 3; j < 48; j++)
+                if (j >= 4 * q0 && j < 4 * q1 && j < 3 * M) row[j] = shr[j - 3];
+        }
+    };
     const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
     const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
     f3 g = mk3(dL_dcolor.x * ((clamp_mask & 1) ? 0.f : 1.f), dL_dcolor.y * ((clamp_mask & 2) ? 0.f : 1.f),
                dL_dcolor.z * ((clamp_mask & 4) ? 0.f : 1.f));
-    auto c = [&](int k) { return mk3(shr[3 * k - 3], shr[3 * k - 2], shr[3 * k - 1]); };   // k >= 1 only
+    auto c = [&](int k) { return mk3(row[3 * k], row[3 * k + 1], row[3 * k + 2]); };   // k >= 1 only
     auto put = [&](int k, float v) { dsh[3 * k] = v * g.x; dsh[3 * k + 1] = v * g.y; dsh[3 * k + 2] = v * g.z; };
     auto axpy = [&](f3& acc, float s, f3 v) { acc.x += s * v.x; acc.y += s * v.y; acc.z += s * v.z; };
     f3 dx = mk3(0, 0, 0), dy = mk3(0, 0, 0), dz = mk3(0, 0, 0);
     put(0, SH_C0);
     int used = 1;
     if (deg > 0) {
+        load_block(0, 3);
         put(1, -SH_C1 * y); put(2, SH_C1 * z); put(3, -SH_C1 * x);
         dx = scale3(-SH_C1, c(3)); dy = scale3(-SH_C1, c(1)); dz = scale3(SH_C1, c(2));
         used = 4;
         if (deg > 1) {
+            load_block(3, 7);
             const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
             put(4, SH_C2[0] * xy); put(5, SH_C2[1] * yz); put(6, SH_C2[2] * (2.f * zz - xx - yy));
             put(7, SH_C2[3] * xz); put(8, SH_C2[4] * (xx - yy));
@@ -524,6 +552,7 @@ __device__ __forceinline__ f3 sh_backward(int deg, int M, const float* __restric
             axpy(dz, SH_C2[1] * y, c(5)); axpy(dz, SH_C2[2] * 2.f * 2.f * z, c(6)); axpy(dz, SH_C2[3] * x, c(7));
             used = 9;
             if (deg > 2) {
+                load_block(7, 12);
                 put(9, SH_C3[0] * y * (3.f * xx - yy)); put(10, SH_C3[1] * xy * z);
                 put(11, SH_C3[2] * y * (4.f * zz - xx - yy)); put(12, SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy));
                 put(13, SH_C3[4] * x * (4.f * zz - xx - yy)); put(14, SH_C3[5] * z * (xx - yy));
@@ -582,8 +611,176 @@ constexpr int PB_SMALL = 25;      // means3D 3, means2D 3, colors 3, opacity 1, 
 constexpr int PB_MAX_M = 16;
 constexpr int PB_SH_STRIDE = PB_MAX_M * 3 + 1;   // odd row stride: conflict-free per-thread writes
 
+// Everything between the blend-stage accumulators of ONE visible Gaussian and its 73 gradient values, staged into
+// `my` (slots: 0-2 means3D, 3-5 means2D, 6-8 colors, 9 opacity, 10-11 scales, 12-15 rots, 16-24 transMat; zeroed by the
+// caller) and `my_sh` (the SH row).
 template <bool RAW>
-__global__ void __launch_bounds__(PB_THREADS) project_bwd_kernel(ProjectBwdArgs a) {
+__device__ __forceinline__ void project_bwd_one(const ProjectBwdArgs& a, int idx, float* __restrict__ my, float* __restrict__ my_sh) {
+    const int M = a.M;
+    // blend-stage accumulators
+    const float4* acc = a.acc + (size_t)idx * ACC_F4;
+    const float4 a0 = acc[0], a1 = acc[1], a2 = acc[2], a3 = acc[3], a4 = acc[4], a5 = acc[5];
+    const float4* rec0 = a.geom.rec + (size_t)idx * REC_F4;
+    float dT[3][3];   // dT[j] = d/d(Tu,Tv,Tw)[j]
+    {
+        // moments of q about the Gaussian's moment origin -> dT (common.cuh, accumulator layout)
+        const float4 r1 = rec0[1], r2 = rec0[2], r3 = rec0[3];
+        const f3 rTu = mk3(r1.x, r1.y, r1.z), rTv = mk3(r1.w, r2.x, r2.y), rTw = mk3(r2.z, r2.w, r3.x);
+        const float ccx = moment_origin(r3.y, (float)(a.W - 1)), ccy = moment_origin(r3.z, (float)(a.H - 1));
+        const f3 kc = sub3(scale3(ccx, rTw), rTu), lc = sub3(scale3(ccy, rTw), rTv);
+        const f3 Q0 = mk3(a0.x, a0.y, a0.z), Qx = mk3(a0.w, a1.x, a1.y), Qy = mk3(a1.z, a1.w, a2.x), Z = mk3(a2.y, a2.z, a2.w);
+        const f3 c1 = cross3(Qy, rTw), c2 = cross3(Q0, lc), c3 = cross3(rTw, Qx), c4 = cross3(kc, Q0);
+        const f3 c5 = cross3(Qx, lc), c6 = cross3(kc, Qy);
+        const f3 dTu = mk3(c1.x + c2.x, c1.y + c2.y, c1.z + c2.z), dTv = mk3(c3.x + c4.x, c3.y + c4.y, c3.z + c4.z);
+        dT[0][0] = dTu.x; dT[0][1] = dTu.y; dT[0][2] = dTu.z;
+        dT[1][0] = dTv.x; dT[1][1] = dTv.y; dT[1][2] = dTv.z;
+        dT[2][0] = Z.x - (ccx * dTu.x + ccy * dTv.x + c5.x + c6.x);
+        dT[2][1] = Z.y - (ccx * dTu.y + ccy * dTv.y + c5.y + c6.y);
+        dT[2][2] = Z.z - (ccx * dTu.z + ccy * dTv.z + c5.z + c6.z);
+    }
+    const float raw_dT[9] = {dT[0][0], dT[0][1], dT[0][2], dT[1][0], dT[1][1], dT[1][2], dT[2][0], dT[2][1], dT[2][2]};
+    const float m2x = a3.x, m2y = a3.y;
+    const f3 dcol = mk3(a3.w, a4.x, a4.y);
+    const f3 dnrm = mk3(a4.z, a4.w, a5.x);
+    my[9] = a3.z;
+    my[6] = dcol.x; my[7] = dcol.y; my[8] = dcol.z;
+
+    // W, H as the reference rebuilds them in fp32 (CR/backward.cu:618-619)
+    const int Wq = int(a.focal_x * a.tan_fovx * 2);
+    const int Hq = int(a.focal_y * a.tan_fovy * 2);
+
+    const float4* rec = a.geom.rec + (size_t)idx * REC_F4;
+    const float4 q1 = rec[1], q2 = rec[2], q3 = rec[3];
+    const bool precomp = (a.scales == nullptr);
+    const f3 p = mk3(a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]);
+    f3 Tu, Tv, Tw, R[3], normal = mk3(0, 0, 0);
+    float sx = 0, sy = 0;
+    float Pm[3][4];
+    float4 quat = make_float4(1, 0, 0, 0);
+    Activated act;
+    act.inv_norm = 1.0f;
+    if (precomp) {
+        Tu = mk3(q1.x, q1.y, q1.z); Tv = mk3(q1.w, q2.x, q2.y); Tw = mk3(q2.z, q2.w, q3.x);
+    } else {
+        float2 sc = ((const float2*)a.scales)[idx];
+        quat = ((const float4*)a.rotations)[idx];
+        if (RAW) {
+            act = activate(sc, quat, a.opacities[idx], a.mip_filter, idx);
+            sc = act.scale; quat = act.rot;
+        }
+        sx = sc.x; sy = sc.y;  // scale_modifier ignored on purpose (quirk 2, CR/backward.cu:481)
+        quat_to_R(quat, R);
+        // P = world2ndc * ndc2pix (mat3x4), T = transpose(M) * P (CR/backward.cu:490-504)
+        const float nd[3][4] = {{float(Wq) / 2.0f, 0, 0, float(Wq - 1) / 2.0f},
+                                {0, float(Hq) / 2.0f, 0, float(Hq - 1) / 2.0f},
+                                {0, 0, 0, 1}};
+        const float* pm = a.proj;
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                Pm[c][k] = pm[0 + 4 * k] * nd[c][0] + pm[1 + 4 * k] * nd[c][1] + pm[2 + 4 * k] * nd[c][2] + pm[3 + 4 * k] * nd[c][3];
+        const f3 L0 = mk3(R[0].x * sx, R[0].y * sx, R[0].z * sx), L1 = mk3(R[1].x * sy, R[1].y * sy, R[1].z * sy);
+        float Tm[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            Tm[c][0] = L0.x * Pm[c][0] + L0.y * Pm[c][1] + L0.z * Pm[c][2];
+            Tm[c][1] = L1.x * Pm[c][0] + L1.y * Pm[c][1] + L1.z * Pm[c][2];
+            Tm[c][2] = p.x * Pm[c][0] + p.y * Pm[c][1] + p.z * Pm[c][2] + Pm[c][3];
+        }
+        Tu = mk3(Tm[0][0], Tm[0][1], Tm[0][2]); Tv = mk3(Tm[1][0], Tm[1][1], Tm[1][2]); Tw = mk3(Tm[2][0], Tm[2][1], Tm[2][2]);
+        normal = xform_vec_4x3(R[2], a.view);
+    }
+    // low-pass centre gradient -> dT (CR/backward.cu:515-541; cutoff-1 approximation, quirk 4)
+    if (m2x != 0 || m2y != 0) {
+        const float distance = Tw.x * Tw.x + Tw.y * Tw.y - Tw.z * Tw.z;
+        const float f = 1 / distance;
+        const float dpx_dT00 = f * Tw.x, dpx_dT01 = f * Tw.y, dpx_dT02 = -f * Tw.z;
+        const float dpx_dT30 = Tu.x * (f - 2 * f * f * Tw.x * Tw.x);
+        const float dpx_dT31 = Tu.y * (f - 2 * f * f * Tw.y * Tw.y);
+        const float dpx_dT32 = -Tu.z * (f + 2 * f * f * Tw.z * Tw.z);
+        const float dpy_dT30 = Tv.x * (f - 2 * f * f * Tw.x * Tw.x);
+        const float dpy_dT31 = Tv.y * (f - 2 * f * f * Tw.y * Tw.y);
+        const float dpy_dT32 = -Tv.z * (f + 2 * f * f * Tw.z * Tw.z);
+        dT[0][0] += m2x * dpx_dT00; dT[0][1] += m2x * dpx_dT01; dT[0][2] += m2x * dpx_dT02;
+        dT[1][0] += m2y * dpx_dT00; dT[1][1] += m2y * dpx_dT01; dT[1][2] += m2y * dpx_dT02;
+        dT[2][0] += m2x * dpx_dT30 + m2y * dpy_dT30;
+        dT[2][1] += m2x * dpx_dT31 + m2y * dpy_dT31;
+        dT[2][2] += m2x * dpx_dT32 + m2y * dpy_dT32;
+    }
+    float proxy2, proxy5;
+    if (precomp) {
+        // dL_dtransMat is the gradient of the precomputed input and feeds the proxy after the
+        // update above (CR/backward.cu:542-553)
+        for (int j = 0; j < 3; j++) for (int c = 0; c < 3; c++) my[16 + 3 * j + c] = dT[j][c];
+        proxy2 = dT[0][2]; proxy5 = dT[1][2];
+    } else {
+        // the reference returns the raw blend-stage accumulator here (dT before the low-pass update above)
+#pragma unroll
+        for (int j = 0; j < 9; j++) my[16 + j] = raw_dT[j];
+        proxy2 = raw_dT[2]; proxy5 = raw_dT[5];
+        // dL_dM[c][k] = sum_j P[j][k] * dT[j][c]
+        float dM[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) dM[c][k] = Pm[0][k] * dT[0][c] + Pm[1][k] * dT[1][c] + Pm[2][k] * dT[2][c];
+        f3 dtn = xform_vec_4x3_T(dnrm, a.view);
+        const f3 pv = xform_point_4x3(p, a.view);
+        const float cosv = -sum3(mul3(pv, normal));
+        const float mult = cosv > 0 ? 1.0f : -1.0f;
+        dtn = scale3(mult, dtn);
+        // dL_dR columns: dRS0 * sx, dRS1 * sy, dtn ; quat_to_rotmat_vjp (CR/auxiliary.h:237-281)
+        const f3 v0 = mk3(dM[0][0] * sx, dM[0][1] * sx, dM[0][2] * sx);
+        const f3 v1 = mk3(dM[1][0] * sy, dM[1][1] * sy, dM[1][2] * sy);
+        const f3 v2 = dtn;
+        const float s = rsqrtf(quat.w * quat.w + quat.x * quat.x + quat.y * quat.y + quat.z * quat.z);
+        const float w = quat.x * s, x = quat.y * s, y = quat.z * s, z = quat.w * s;
+        const float vR00 = v0.x, vR01 = v0.y, vR02 = v0.z, vR10 = v1.x, vR11 = v1.y, vR12 = v1.z, vR20 = v2.x, vR21 = v2.y, vR22 = v2.z;
+        my[12] = 2.f * (x * (vR12 - vR21) + y * (vR20 - vR02) + z * (vR01 - vR10));
+        my[13] = 2.f * (-2.f * x * (vR11 + vR22) + y * (vR01 + vR10) + z * (vR02 + vR20) + w * (vR12 - vR21));
+        my[14] = 2.f * (x * (vR01 + vR10) - 2.f * y * (vR00 + vR22) + z * (vR12 + vR21) + w * (vR20 - vR02));
+        my[15] = 2.f * (x * (vR02 + vR20) + y * (vR12 + vR21) - 2.f * z * (vR00 + vR11) + w * (vR01 - vR10));
+        my[10] = dM[0][0] * R[0].x + dM[0][1] * R[0].y + dM[0][2] * R[0].z;
+        my[11] = dM[1][0] * R[1].x + dM[1][1] * R[1].y + dM[1][2] * R[1].z;
+        my[0] = dM[2][0]; my[1] = dM[2][1]; my[2] = dM[2][2];
+    }
+    if (a.shs) {
+        const f3 dir = sub3(p, mk3(a.campos[0], a.campos[1], a.campos[2]));
+        const float* shr = RAW ? a.sh_rest + (size_t)idx * (M - 1) * 3 : a.shs + (size_t)idx * M * 3 + 3;
+        // whole-row vector loads when the [M][3] rows are 192 bytes on a 16-byte aligned base
+        const float4* row4 = (!RAW && M == 16 && (reinterpret_cast<uintptr_t>(a.shs) & 15u) == 0)
+                                 ? reinterpret_cast<const float4*>(a.shs + (size_t)idx * 48) : nullptr;
+        const f3 dmean = sh_backward(a.D, M, shr, row4, dir, a.geom.clamped[idx], dcol, my_sh);
+        my[0] += dmean.x; my[1] += dmean.y; my[2] += dmean.z;
+    }
+    if (RAW && !precomp) {
+        // chain rule through the activations (what autograd does after the reference operator):
+        //   exp:        d/d_scaling = g e            [mip: scale = sqrt(e^2 + f^2): g e^2 / scale,
+        //               plus the opacity's dependence on the scales: g_o opacity f^2 / (e^2 + f^2)]
+        //   sigmoid:    d/d_opacity = g_o coef sig (1 - sig)
+        //   normalize:  d/d_rotation = (g - q (q . g)) / max(|r|, eps)
+        const float g_o = my[9];
+        if (a.mip_filter != nullptr) {
+            my[10] = my[10] * act.e2.x / act.scale.x + g_o * act.opacity * act.f2 / (act.e2.x + act.f2);
+            my[11] = my[11] * act.e2.y / act.scale.y + g_o * act.opacity * act.f2 / (act.e2.y + act.f2);
+        } else {
+            my[10] *= act.scale.x;
+            my[11] *= act.scale.y;
+        }
+        my[9] = g_o * act.coef * act.sig * (1.0f - act.sig);
+        const float qg = quat.x * my[12] + quat.y * my[13] + quat.z * my[14] + quat.w * my[15];
+        my[12] = (my[12] - quat.x * qg) * act.inv_norm; my[13] = (my[13] - quat.y * qg) * act.inv_norm;
+        my[14] = (my[14] - quat.z * qg) * act.inv_norm; my[15] = (my[15] - quat.w * qg) * act.inv_norm;
+    }
+    // densification proxy (CR/backward.cu:637-640, quirk 5): depth = forward T[8]
+    const float depth = q3.x;
+    my[3] = proxy2 * depth * 0.5f * float(Wq);
+    my[4] = proxy5 * depth * 0.5f * float(Hq);
+}
+
+template <bool RAW>
+__global__ void __launch_bounds__(PB_THREADS, 6) project_bwd_kernel(ProjectBwdArgs a) {
     __shared__ float s_sh[PB_WARPS][32 * PB_SH_STRIDE];
     __shared__ float s_small[PB_WARPS][32 * PB_SMALL];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -600,165 +797,7 @@ __global__ void __launch_bounds__(PB_THREADS) project_bwd_kernel(ProjectBwdArgs 
     const bool visible = idx < a.P && a.radii[idx] > 0;
     // Gaussians without an SH gradient are written as zeros straight from registers below
     const unsigned sh_rows = __ballot_sync(0xffffffffu, visible && a.shs != nullptr);
-    if (visible) {
-        // blend-stage accumulators
-        const float4* acc = a.acc + (size_t)idx * ACC_F4;
-        const float4 a0 = acc[0], a1 = acc[1], a2 = acc[2], a3 = acc[3], a4 = acc[4], a5 = acc[5];
-        const float4* rec0 = a.geom.rec + (size_t)idx * REC_F4;
-        float dT[3][3];   // dT[j] = d/d(Tu,Tv,Tw)[j]
-        {
-            // moments of q about the Gaussian's moment origin -> dT (common.cuh, accumulator layout)
-            const float4 r1 = rec0[1], r2 = rec0[2], r3 = rec0[3];
-            const f3 rTu = mk3(r1.x, r1.y, r1.z), rTv = mk3(r1.w, r2.x, r2.y), rTw = mk3(r2.z, r2.w, r3.x);
-            const float ccx = moment_origin(r3.y, (float)(a.W - 1)), ccy = moment_origin(r3.z, (float)(a.H - 1));
-            const f3 kc = sub3(scale3(ccx, rTw), rTu), lc = sub3(scale3(ccy, rTw), rTv);
-            const f3 Q0 = mk3(a0.x, a0.y, a0.z), Qx = mk3(a0.w, a1.x, a1.y), Qy = mk3(a1.z, a1.w, a2.x), Z = mk3(a2.y, a2.z, a2.w);
-            const f3 c1 = cross3(Qy, rTw), c2 = cross3(Q0, lc), c3 = cross3(rTw, Qx), c4 = cross3(kc, Q0);
-            const f3 c5 = cross3(Qx, lc), c6 = cross3(kc, Qy);
-            const f3 dTu = mk3(c1.x + c2.x, c1.y + c2.y, c1.z + c2.z), dTv = mk3(c3.x + c4.x, c3.y + c4.y, c3.z + c4.z);
-            dT[0][0] = dTu.x; dT[0][1] = dTu.y; dT[0][2] = dTu.z;
-            dT[1][0] = dTv.x; dT[1][1] = dTv.y; dT[1][2] = dTv.z;
-            dT[2][0] = Z.x - (ccx * dTu.x + ccy * dTv.x + c5.x + c6.x);
-            dT[2][1] = Z.y - (ccx * dTu.y + ccy * dTv.y + c5.y + c6.y);
-            dT[2][2] = Z.z - (ccx * dTu.z + ccy * dTv.z + c5.z + c6.z);
-        }
-        const float raw_dT[9] = {dT[0][0], dT[0][1], dT[0][2], dT[1][0], dT[1][1], dT[1][2], dT[2][0], dT[2][1], dT[2][2]};
-        const float m2x = a3.x, m2y = a3.y;
-        const f3 dcol = mk3(a3.w, a4.x, a4.y);
-        const f3 dnrm = mk3(a4.z, a4.w, a5.x);
-        my[9] = a3.z;
-        my[6] = dcol.x; my[7] = dcol.y; my[8] = dcol.z;
-
-        // W, H as the reference rebuilds them in fp32 (CR/backward.cu:618-619)
-        const int Wq = int(a.focal_x * a.tan_fovx * 2);
-        const int Hq = int(a.focal_y * a.tan_fovy * 2);
-
-        const float4* rec = a.geom.rec + (size_t)idx * REC_F4;
-        const float4 q1 = rec[1], q2 = rec[2], q3 = rec[3];
-        const bool precomp = (a.scales == nullptr);
-        const f3 p = mk3(a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]);
-        f3 Tu, Tv, Tw, R[3], normal = mk3(0, 0, 0);
-        float sx = 0, sy = 0;
-        float Pm[3][4];
-        float4 quat = make_float4(1, 0, 0, 0);
-        Activated act;
-        act.inv_norm = 1.0f;
-        if (precomp) {
-            Tu = mk3(q1.x, q1.y, q1.z); Tv = mk3(q1.w, q2.x, q2.y); Tw = mk3(q2.z, q2.w, q3.x);
-        } else {
-            float2 sc = ((const float2*)a.scales)[idx];
-            quat = ((const float4*)a.rotations)[idx];
-            if (RAW) {
-                act = activate(sc, quat, a.opacities[idx], a.mip_filter, idx);
-                sc = act.scale; quat = act.rot;
-            }
-            sx = sc.x; sy = sc.y;  // scale_modifier ignored on purpose (quirk 2, CR/backward.cu:481)
-            quat_to_R(quat, R);
-            // P = world2ndc * ndc2pix (mat3x4), T = transpose(M) * P (CR/backward.cu:490-504)
-            const float nd[3][4] = {{float(Wq) / 2.0f, 0, 0, float(Wq - 1) / 2.0f},
-                                    {0, float(Hq) / 2.0f, 0, float(Hq - 1) / 2.0f},
-                                    {0, 0, 0, 1}};
-            const float* pm = a.proj;
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    Pm[c][k] = pm[0 + 4 * k] * nd[c][0] + pm[1 + 4 * k] * nd[c][1] + pm[2 + 4 * k] * nd[c][2] + pm[3 + 4 * k] * nd[c][3];
-            const f3 L0 = mk3(R[0].x * sx, R[0].y * sx, R[0].z * sx), L1 = mk3(R[1].x * sy, R[1].y * sy, R[1].z * sy);
-            float Tm[3][3];
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                Tm[c][0] = L0.x * Pm[c][0] + L0.y * Pm[c][1] + L0.z * Pm[c][2];
-                Tm[c][1] = L1.x * Pm[c][0] + L1.y * Pm[c][1] + L1.z * Pm[c][2];
-                Tm[c][2] = p.x * Pm[c][0] + p.y * Pm[c][1] + p.z * Pm[c][2] + Pm[c][3];
-            }
-            Tu = mk3(Tm[0][0], Tm[0][1], Tm[0][2]); Tv = mk3(Tm[1][0], Tm[1][1], Tm[1][2]); Tw = mk3(Tm[2][0], Tm[2][1], Tm[2][2]);
-            normal = xform_vec_4x3(R[2], a.view);
-        }
-        // low-pass centre gradient -> dT (CR/backward.cu:515-541; cutoff-1 approximation, quirk 4)
-        if (m2x != 0 || m2y != 0) {
-            const float distance = Tw.x * Tw.x + Tw.y * Tw.y - Tw.z * Tw.z;
-            const float f = 1 / distance;
-            const float dpx_dT00 = f * Tw.x, dpx_dT01 = f * Tw.y, dpx_dT02 = -f * Tw.z;
-            const float dpx_dT30 = Tu.x * (f - 2 * f * f * Tw.x * Tw.x);
-            const float dpx_dT31 = Tu.y * (f - 2 * f * f * Tw.y * Tw.y);
-            const float dpx_dT32 = -Tu.z * (f + 2 * f * f * Tw.z * Tw.z);
-            const float dpy_dT30 = Tv.x * (f - 2 * f * f * Tw.x * Tw.x);
-            const float dpy_dT31 = Tv.y * (f - 2 * f * f * Tw.y * Tw.y);
-            const float dpy_dT32 = -Tv.z * (f + 2 * f * f * Tw.z * Tw.z);
-            dT[0][0] += m2x * dpx_dT00; dT[0][1] += m2x * dpx_dT01; dT[0][2] += m2x * dpx_dT02;
-            dT[1][0] += m2y * dpx_dT00; dT[1][1] += m2y * dpx_dT01; dT[1][2] += m2y * dpx_dT02;
-            dT[2][0] += m2x * dpx_dT30 + m2y * dpy_dT30;
-            dT[2][1] += m2x * dpx_dT31 + m2y * dpy_dT31;
-            dT[2][2] += m2x * dpx_dT32 + m2y * dpy_dT32;
-        }
-        float proxy2, proxy5;
-        if (precomp) {
-            // dL_dtransMat is the gradient of the precomputed input and feeds the proxy after the
-            // update above (CR/backward.cu:542-553)
-            for (int j = 0; j < 3; j++) for (int c = 0; c < 3; c++) my[16 + 3 * j + c] = dT[j][c];
-            proxy2 = dT[0][2]; proxy5 = dT[1][2];
-        } else {
-            // the reference returns the raw blend-stage accumulator here (dT before the low-pass update above)
-#pragma unroll
-            for (int j = 0; j < 9; j++) my[16 + j] = raw_dT[j];
-            proxy2 = raw_dT[2]; proxy5 = raw_dT[5];
-            // dL_dM[c][k] = sum_j P[j][k] * dT[j][c]
-            float dM[3][3];
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-#pragma unroll
-                for (int k = 0; k < 3; k++) dM[c][k] = Pm[0][k] * dT[0][c] + Pm[1][k] * dT[1][c] + Pm[2][k] * dT[2][c];
-            f3 dtn = xform_vec_4x3_T(dnrm, a.view);
-            const f3 pv = xform_point_4x3(p, a.view);
-            const float cosv = -sum3(mul3(pv, normal));
-            const float mult = cosv > 0 ? 1.0f : -1.0f;
-            dtn = scale3(mult, dtn);
-            // dL_dR columns: dRS0 * sx, dRS1 * sy, dtn ; quat_to_rotmat_vjp (CR/auxiliary.h:237-281)
-            const f3 v0 = mk3(dM[0][0] * sx, dM[0][1] * sx, dM[0][2] * sx);
-            const f3 v1 = mk3(dM[1][0] * sy, dM[1][1] * sy, dM[1][2] * sy);
-            const f3 v2 = dtn;
-            const float s = rsqrtf(quat.w * quat.w + quat.x * quat.x + quat.y * quat.y + quat.z * quat.z);
-            const float w = quat.x * s, x = quat.y * s, y = quat.z * s, z = quat.w * s;
-            const float vR00 = v0.x, vR01 = v0.y, vR02 = v0.z, vR10 = v1.x, vR11 = v1.y, vR12 = v1.z, vR20 = v2.x, vR21 = v2.y, vR22 = v2.z;
-            my[12] = 2.f * (x * (vR12 - vR21) + y * (vR20 - vR02) + z * (vR01 - vR10));
-            my[13] = 2.f * (-2.f * x * (vR11 + vR22) + y * (vR01 + vR10) + z * (vR02 + vR20) + w * (vR12 - vR21));
-            my[14] = 2.f * (x * (vR01 + vR10) - 2.f * y * (vR00 + vR22) + z * (vR12 + vR21) + w * (vR20 - vR02));
-            my[15] = 2.f * (x * (vR02 + vR20) + y * (vR12 + vR21) - 2.f * z * (vR00 + vR11) + w * (vR01 - vR10));
-            my[10] = dM[0][0] * R[0].x + dM[0][1] * R[0].y + dM[0][2] * R[0].z;
-            my[11] = dM[1][0] * R[1].x + dM[1][1] * R[1].y + dM[1][2] * R[1].z;
-            my[0] = dM[2][0]; my[1] = dM[2][1]; my[2] = dM[2][2];
-        }
-        if (a.shs) {
-            const f3 dir = sub3(p, mk3(a.campos[0], a.campos[1], a.campos[2]));
-            const float* shr = RAW ? a.sh_rest + (size_t)idx * (M - 1) * 3 : a.shs + (size_t)idx * M * 3 + 3;
-            const f3 dmean = sh_backward(a.D, M, shr, dir, a.geom.clamped[idx], dcol, my_sh);
-            my[0] += dmean.x; my[1] += dmean.y; my[2] += dmean.z;
-        }
-        if (RAW && !precomp) {
-            // chain rule through the activations (what autograd does after the reference operator):
-            //   exp:        d/d_scaling = g e            [mip: scale = sqrt(e^2 + f^2): g e^2 / scale,
-            //               plus the opacity's dependence on the scales: g_o opacity f^2 / (e^2 + f^2)]
-            //   sigmoid:    d/d_opacity = g_o coef sig (1 - sig)
-            //   normalize:  d/d_rotation = (g - q (q . g)) / max(|r|, eps)
-            const float g_o = my[9];
-            if (a.mip_filter != nullptr) {
-                my[10] = my[10] * act.e2.x / act.scale.x + g_o * act.opacity * act.f2 / (act.e2.x + act.f2);
-                my[11] = my[11] * act.e2.y / act.scale.y + g_o * act.opacity * act.f2 / (act.e2.y + act.f2);
-            } else {
-                my[10] *= act.scale.x;
-                my[11] *= act.scale.y;
-            }
-            my[9] = g_o * act.coef * act.sig * (1.0f - act.sig);
-            const float qg = quat.x * my[12] + quat.y * my[13] + quat.z * my[14] + quat.w * my[15];
-            my[12] = (my[12] - quat.x * qg) * act.inv_norm; my[13] = (my[13] - quat.y * qg) * act.inv_norm;
-            my[14] = (my[14] - quat.z * qg) * act.inv_norm; my[15] = (my[15] - quat.w * qg) * act.inv_norm;
-        }
-        // densification proxy (CR/backward.cu:637-640, quirk 5): depth = forward T[8]
-        const float depth = q3.x;
-        my[3] = proxy2 * depth * 0.5f * float(Wq);
-        my[4] = proxy5 * depth * 0.5f * float(Hq);
-    }
+    if (visible) project_bwd_one<RAW>(a, idx, my, my_sh);
     __syncwarp();
     // ---- coalesced write-out of the warp's 32 Gaussians ---------------------------------------
     // accumulate bit set: the destination is a running sum over views (view_parallel's flat gradient
@@ -904,6 +943,83 @@ void launch_multimem_allreduce(float* mc, size_t n_floats, int* mc_max, size_t n
     count_launch();
 }
 
+// The same backward for callers that ACCUMULATE every parameter gradient (view_parallel's gradient sink: rows of
+// invisible Gaussians are not touched at all).  A view sees a fraction of the Gaussians (a quarter at c2), and the kernel
+// above spends ~1900 instructions per warp of 32 consecutive rows whatever the number of live lanes; this one walks the
+// forward's list of visible Gaussians instead, 32 of them per warp, and adds each staged row to wherever its Gaussian
+// lives.  Outputs that are not accumulated (dL_dmeans2D, dL_dcolors, dL_dtransMat) are cleared by the launcher and the
+// visible rows stored.  Warps are independent: no block barrier.
+template <bool RAW>
+__global__ void __launch_bounds__(PB_THREADS, 6) project_bwd_compact_kernel(ProjectBwdArgs a) {
+    __shared__ float s_sh[PB_WARPS][32 * PB_SH_STRIDE];
+    __shared__ float s_small[PB_WARPS][32 * PB_SMALL];
+    __shared__ int s_gid[PB_WARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int V = a.counters[CNT_VISIBLE];
+    const int M = a.M;
+    const bool mc = (a.accumulate & ACC_MULTIMEM) != 0;
+    float* my_sh = &s_sh[warp][lane * PB_SH_STRIDE];
+    float* my = &s_small[warp][lane * PB_SMALL];
+    {
+        const int base = (blockIdx.x * PB_WARPS + warp) * 32;
+        if (base >= V) return;
+        const int k = base + lane;
+        int idx = k < V ? (int)a.geom.visible_list[k] : -1;
+        if (idx >= 0 && a.radii[idx] <= 0) idx = -1;          // the dense kernel's definition of "visible"
+#pragma unroll
+        for (int i = 0; i < PB_SMALL; i++) my[i] = 0.f;
+        s_gid[warp][lane] = idx;
+        if (idx >= 0) project_bwd_one<RAW>(a, idx, my, my_sh);
+        __syncwarp();
+        // small outputs: element e of the warp's [32][width] block -> row e / width of the staging
+        auto scatter_out = [&](float* dst, int width, int slot, bool accumulate) {
+            for (int e = lane; e < 32 * width; e += 32) {
+                const int row = e / width, c = e - row * width;
+                const int g = s_gid[warp][row];
+                if (g < 0) continue;
+                const float v = s_small[warp][row * PB_SMALL + slot + c];
+                float* d = dst + (size_t)g * width + c;
+                if (accumulate) red_add(d, v, mc);
+                else *d = v;
+            }
+        };
+        scatter_out(a.dL_dmeans3D, 3, 0, true);
+        scatter_out(a.dL_dmeans2D, 3, 3, false);
+        if (a.dL_dcolors) scatter_out(a.dL_dcolors, 3, 6, false);
+        scatter_out(a.dL_dopacity, 1, 9, true);
+        scatter_out(a.dL_dscales, 2, 10, true);
+        scatter_out(a.dL_drots, 4, 12, true);
+        if (a.dL_dtransMat) scatter_out(a.dL_dtransMat, 9, 16, false);
+        if (a.dL_dsh != nullptr) {
+            auto scatter_sh = [&](float* dst, int rowlen, int src_off) {
+                if ((rowlen & 3) == 0 && src_off == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+                    const int quads = rowlen >> 2;                       // 16 bytes per reduction
+                    for (int f = lane; f < 32 * quads; f += 32) {
+                        const int row = f / quads, c4 = (f - row * quads) * 4;
+                        const int g = s_gid[warp][row];
+                        if (g < 0) continue;
+                        const float* src = &s_sh[warp][row * PB_SH_STRIDE + c4];
+                        red_add4(dst + (size_t)g * rowlen + c4, make_float4(src[0], src[1], src[2], src[3]), mc);
+                    }
+                } else {
+                    for (int e = lane; e < 32 * rowlen; e += 32) {
+                        const int row = e / rowlen, c = e - row * rowlen;
+                        const int g = s_gid[warp][row];
+                        if (g < 0) continue;
+                        red_add(dst + (size_t)g * rowlen + c, s_sh[warp][row * PB_SH_STRIDE + src_off + c], mc);
+                    }
+                }
+            };
+            if (RAW) {
+                scatter_sh(a.dL_dsh, 3, 0);
+                if (M > 1) scatter_sh(a.dL_dsh_rest, (M - 1) * 3, 3);
+            } else {
+                scatter_sh(a.dL_dsh, M * 3, 0);
+            }
+        }
+    }
+}
+
 // Zero the blend-stage accumulator rows of the visible Gaussians only (the others are never read):
 // 4 B read per Gaussian + 80 B written per visible one, instead of an 80 P byte memset.
 __global__ void __launch_bounds__(256) acc_clear_kernel(int P, const int* __restrict__ radii, float4* __restrict__ acc) {
@@ -941,6 +1057,20 @@ void launch_scatter(const ScatterArgs& a, cudaStream_t s) {
 }
 void launch_project_bwd(const ProjectBwdArgs& a, cudaStream_t s) {
     if (a.P <= 0) return;
+    // every parameter gradient accumulated (the gradient sink of view_parallel): walk the visible list
+    constexpr int ACC_ALL = ACC_MEANS3D | ACC_SH | ACC_OPACITY | ACC_SCALES | ACC_ROTATIONS;
+    if ((a.accumulate & ACC_ALL) == ACC_ALL && a.counters != nullptr) {
+        cudaMemsetAsync(a.dL_dmeans2D, 0, sizeof(float) * 3 * (size_t)a.P, s);
+        if (a.dL_dcolors) cudaMemsetAsync(a.dL_dcolors, 0, sizeof(float) * 3 * (size_t)a.P, s);
+        if (a.dL_dtransMat) cudaMemsetAsync(a.dL_dtransMat, 0, sizeof(float) * 9 * (size_t)a.P, s);
+        // the number of visible Gaussians is known on the device only: one CTA per 128 Gaussians, the CTAs past the
+        // end of the list read one counter and leave
+        const int grid = (a.P + PB_THREADS - 1) / PB_THREADS;
+        if (a.raw) project_bwd_compact_kernel<true><<<grid, PB_THREADS, 0, s>>>(a);
+        else project_bwd_compact_kernel<false><<<grid, PB_THREADS, 0, s>>>(a);
+        count_launch();
+        return;
+    }
     if (a.raw) project_bwd_kernel<true><<<(a.P + PB_THREADS - 1) / PB_THREADS, PB_THREADS, 0, s>>>(a);
     else project_bwd_kernel<false><<<(a.P + PB_THREADS - 1) / PB_THREADS, PB_THREADS, 0, s>>>(a);
     count_launch();

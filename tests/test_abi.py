@@ -37,9 +37,9 @@ def test_version_and_sizes():
     from g4splat_b200 import _lib
     lib = _lib.load()
     assert lib.g4s_version() == 100
-    # 112-byte record + depth + count + rect + clamp mask per Gaussian, 256-byte aligned sections
+    # 112-byte record + depth + count + rect + clamp mask + visible-list slot per Gaussian, 256-byte aligned sections
     g = lib.g4s_geom_bytes(1000)
-    assert 1000 * (112 + 4 + 4 + 8 + 1) <= g <= 1000 * (112 + 4 + 4 + 8 + 1) + 5 * 256
+    assert 1000 * (112 + 4 + 4 + 8 + 1 + 4) <= g <= 1000 * (112 + 4 + 4 + 8 + 1 + 4) + 6 * 256
     assert lib.g4s_geom_bytes(0) > 0
     n = 1920 * 1080
     assert lib.g4s_image_bytes(1920, 1080) >= n * 20
