@@ -47,6 +47,7 @@ SIGNATURES = {
     "g4s_depth_order_backward": (_i, [_i, _i, _vp, _vp, _vp, _f, _i, _i, _f, _vp, _vp, _f, _vp, _vp]),
     "g4s_mip_filter": (_i, [_i, _vp, _i, _vp, _f, _f, _f, _vp, _vp, _vp]),
     "g4s_profile_enable": (_i, [_i]),
+    "g4s_profile_select": (_i, [C.c_uint]),
     "g4s_profile_num_stages": (_i, []),
     "g4s_profile_stage_name": (C.c_char_p, [_i]),
     "g4s_profile_read": (_i, [_vp, _vp, _i]),

@@ -40,6 +40,7 @@ enum { ST_PROJECT_FWD = 0, ST_TILE_SCAN, ST_SCATTER, ST_TILE_SORT, ST_BLEND_FWD,
 static const char* const kStageNames[ST_COUNT] = {"project_fwd", "tile_scan", "scatter", "tile_sort", "blend_fwd",
                                                   "acc_clear", "blend_bwd", "project_bwd"};
 static bool g_profile = false;
+static unsigned g_profile_mask = ~0u;     // stages that are bracketed while g_profile is on (g4s_profile_select)
 // A small ring of event pairs per stage: a slot is folded into the running mean when it comes up
 // for reuse, RING launches later, by which time it has completed even when the host runs ahead of
 // the device by a whole view.
@@ -59,16 +60,17 @@ static void harvest(int stage, int slot, bool wait) {
     g_ev_valid[stage][slot] = false;
 }
 struct StageTimer {
-    int stage, slot; cudaStream_t s;
-    StageTimer(int st, cudaStream_t stream) : stage(st), slot(0), s(stream) {
-        if (g_profile) {
+    int stage, slot; cudaStream_t s; bool on;
+    StageTimer(int st, cudaStream_t stream) : stage(st), slot(0), s(stream), on(false) {
+        on = g_profile && ((g_profile_mask >> stage) & 1u);
+        if (on) {
             slot = (int)(g_ev_next[stage]++ % EV_RING);
             harvest(stage, slot, false);
             cudaEventRecord(g_ev_begin[stage][slot], s);
         }
     }
     ~StageTimer() {
-        if (g_profile) { cudaEventRecord(g_ev_end[stage][slot], s); g_ev_valid[stage][slot] = true; }
+        if (on) { cudaEventRecord(g_ev_end[stage][slot], s); g_ev_valid[stage][slot] = true; }
     }
 };
 }  // namespace g4s
@@ -92,6 +94,7 @@ int g4s_profile_enable(int on) {
     }
     return G4S_OK;
 }
+int g4s_profile_select(unsigned stage_mask) { g_profile_mask = stage_mask; return G4S_OK; }
 int g4s_profile_num_stages(void) { return ST_COUNT; }
 const char* g4s_profile_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : ""; }
 int g4s_profile_read(float* mean_ms_out, int64_t* count_out, int n) {

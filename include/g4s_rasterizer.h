@@ -345,6 +345,11 @@ int64_t g4s_launch_count(void);
  * last g4s_profile_enable.  Stage order:
  * project_fwd, tile_scan, scatter, tile_sort, blend_fwd, acc_clear, blend_bwd, project_bwd. */
 int g4s_profile_enable(int on);
+/* Bit i set: stage i is bracketed while profiling is on (default: all).  Every bracket is two event records
+ * on the stream, i.e. two points where consecutive kernels cannot overlap their launch: measured on a B200, bracketing
+ * all eight stages of a 1.5 ms view costs 2.8 % of the throughput, so a benchmark brackets everything in an untimed
+ * pass and only the kernel its roofline is about inside the timed region. */
+int g4s_profile_select(unsigned stage_mask);
 int g4s_profile_num_stages(void);
 const char* g4s_profile_stage_name(int i);
 int g4s_profile_read(float* mean_ms_out, int64_t* count_out, int n);
