@@ -122,3 +122,24 @@ def test_scatter_owner_search_lands_on_the_live_lane():
         for i in range(sum(counts)):
             lane = scatter_owner(excl, i)
             assert counts[lane] > 0 and excl[lane] <= i < excl[lane] + counts[lane]
+
+
+def bucket_of(c):
+    """binning.cu: tile_scan_kernel -- two buckets per octave of the list length, longest first; empty tiles last."""
+    if c == 0:
+        return 63
+    lg = c.bit_length() - 1
+    half = ((c >> (lg - 1)) & 1) if lg > 0 else 0
+    return max(0, 64 - 2 - (2 * lg + half))
+
+
+def test_long_list_prefix_of_the_tile_order():
+    """tile_sort_kernel's long-list CTAs walk tile_order[0 : counters[CNT_LONG_TILES]], the base of bucket LONG_BUCKET_END
+    = 47: that prefix must hold every tile with more than 256 entries (and may hold tiles with exactly 256, which the
+    long-list role skips and a warp sorts)."""
+    assert all(bucket_of(c) < 47 for c in list(range(256, 5000)) + [10 ** 5, 10 ** 6, 2 ** 31 - 1])
+    assert all(bucket_of(c) >= 47 for c in range(0, 256))
+    # buckets descend with the length, so a counting sort by bucket is longest-first to within one half-octave
+    lengths = [0, 1, 2, 3, 5, 31, 32, 100, 255, 256, 257, 383, 384, 794, 1024, 4097, 70000]
+    buckets = [bucket_of(c) for c in lengths]
+    assert buckets == sorted(buckets, reverse=True)
